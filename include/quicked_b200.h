@@ -1,0 +1,105 @@
+/*
+ * include/quicked_b200.h — additive batched C-ABI of the B200-native QuickEd path.
+ *
+ * The reference library aligns one pair per quicked_align() call; its only batching is the OpenMP loop in
+ * the benchmark tool (reference: tools/align_benchmark/align_benchmark.c:232-306) over a packed
+ * sequence buffer + offsets (reference: tools/align_benchmark/benchmark/sequence_buffer.h:30-50).  A GPU
+ * needs the whole batch at once, so this header adds a batched entry point with that same packed layout.
+ * quicked_align() (include/quicked.h) is a batch of one through the same code.
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  All functions return 0 on success or a
+ * negative qb200 error code; per-pair outcomes are quicked_status_t values in `status[]`.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with QB200_ERR_NO_DEVICE.
+ */
+#ifndef QUICKED_B200_H
+#define QUICKED_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "quicked.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    QB200_OK = 0,
+    QB200_ERR_NO_DEVICE = -100,   /* no CUDA device / driver: the product path refuses to run */
+    QB200_ERR_CUDA = -101,        /* a CUDA call failed; see qb200_last_error() */
+    QB200_ERR_ARG = -102,
+    QB200_ERR_OOM = -103,
+    QB200_ERR_CAPACITY = -104,    /* caller's cigar buffer too small; *cigar_bytes holds the size needed */
+};
+
+typedef struct qb200_ctx qb200_ctx_t;
+
+/* A batch of pairs: sequence i is seqs[off[i] .. off[i]+len[i]).  Mirrors sequence_buffer_t
+ * (reference sequence_buffer.h:30-50): one packed character buffer plus per-pair offsets and lengths.
+ * Bytes are raw ASCII exactly as the reference takes them (dna_encode semantics, reference dna_text.c:41-46). */
+typedef struct {
+    const char    *seqs;          /* packed characters                                   */
+    int64_t        seqs_bytes;
+    int64_t        n_pairs;
+    const int64_t *pattern_off;   /* [n_pairs] */
+    const int32_t *pattern_len;   /* [n_pairs] */
+    const int64_t *text_off;      /* [n_pairs] */
+    const int32_t *text_len;      /* [n_pairs] */
+} qb200_batch_t;
+
+/* Caller-provided result buffers (host memory for *_host calls). */
+typedef struct {
+    int32_t *score;               /* [n_pairs] aligner->score of each pair                               */
+    int32_t *status;              /* [n_pairs] quicked_status_t of each pair                             */
+    char    *cigar;               /* packed NUL-terminated CIGAR strings; may be NULL when only_score     */
+    int64_t  cigar_capacity;      /* bytes available at `cigar`                                           */
+    int64_t *cigar_off;           /* [n_pairs+1] string i is cigar[cigar_off[i] .. cigar_off[i+1]-1) + NUL */
+    int64_t  cigar_bytes;         /* out: bytes written (or needed, with QB200_ERR_CAPACITY)              */
+} qb200_results_t;
+
+typedef struct {                  /* counters of the last qb200_run(); all times are CUDA-event ms */
+    int64_t n_pairs;
+    int64_t kernel_launches;      /* our own kernels launched by the last run                              */
+    int64_t word_steps;           /* 64-row x 1-column Myers block updates executed (device-counted)       */
+    int64_t word_steps_windowed, word_steps_banded;
+    int64_t cells;                /* sum of m*n over the batch (GCUPS_equiv numerator)                     */
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t pairs_stage2, pairs_stage3, banded_tries, hirschberg_splits, leaves;
+    float   ms_total, ms_prepare, ms_windowed_s, ms_windowed_l, ms_banded, ms_align_fill, ms_align_trace,
+            ms_cigar;
+    int64_t matrix_bytes;         /* traceback state written to HBM (Pv/Mv columns)                        */
+} qb200_stats_t;
+
+/* --- context --- */
+int  qb200_device_count(void);                                   /* 0 when no usable CUDA device          */
+int  qb200_create(qb200_ctx_t **ctx, int device);                /* one context per GPU / host thread     */
+void qb200_destroy(qb200_ctx_t *ctx);
+int  qb200_set_stream(qb200_ctx_t *ctx, void *cuda_stream);     /* launch on the caller's stream (e.g. torch's) */
+int  qb200_set_workspace_limit(qb200_ctx_t *ctx, size_t bytes); /* cap for the traceback-state pool (default 48 GiB) */
+const char *qb200_last_error(qb200_ctx_t *ctx);
+
+/* --- three-phase batch API: upload (H2D) -> run (kernels only) -> download (D2H) --- */
+int qb200_upload(qb200_ctx_t *ctx, const qb200_batch_t *host_batch);             /* pageable or pinned host memory */
+int qb200_upload_device(qb200_ctx_t *ctx, const qb200_batch_t *device_batch);    /* arrays already in HBM: no copy */
+int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params);                  /* results stay in HBM           */
+int qb200_download(qb200_ctx_t *ctx, qb200_results_t *host_results);
+int qb200_get_stats(qb200_ctx_t *ctx, qb200_stats_t *stats);
+
+/* --- one call, host in / host out: what a reference caller's batch loop is replaced by --- */
+int qb200_align_batch(qb200_ctx_t *ctx, const quicked_params_t *params,
+                      const qb200_batch_t *host_batch, qb200_results_t *host_results);
+
+/* --- pinned host staging helpers (cudaHostAlloc / cudaFreeHost) --- */
+void *qb200_host_alloc(size_t bytes);
+void  qb200_host_free(void *p);
+
+/* --- seeded twin of the reference's generate_dataset edit model (reference generate_dataset.c:108-199,366-410):
+ * fills a packed batch (pattern i then text i, back to back) in host memory.  Returns bytes written to seqs,
+ * or a negative error.  seqs must hold n_pairs * (2*length + ceil(length*error) + 2) bytes. */
+int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, double error,
+                             char *seqs, int64_t *pattern_off, int32_t *pattern_len,
+                             int64_t *text_off, int32_t *text_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUICKED_B200_H */

@@ -1,0 +1,286 @@
+"""ctypes bindings of the C-ABI declared in include/quicked.h and include/quicked_b200.h.
+
+This is the Python host-side mirror of the reference's operator interface:
+  * `QuickedAligner` has the method surface of the reference's C++/pybind11 class
+    (reference bindings/cpp/quicked.hpp:46-73, bindings/python/quicked.cpp:30-64): align, set*, getScore, getCigar;
+  * `BatchAligner` is the additive batched entry point (one GPU context, packed batch in, scores + CIGARs out).
+
+The product path has no CPU fallback: loading fails loudly when libquicked_b200.so is missing, and every compute
+call raises when there is no CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libquicked_b200.so")
+
+QUICKED, WINDOWED, BANDED, HIRSCHBERG = 0, 1, 2, 3
+QUICKED_OK, QUICKED_ERROR, QUICKED_FAIL_NON_CONVERGENCE = 0, -1, -2
+QUICKED_UNKNOWN_ALGO, QUICKED_EMPTY_SEQUENCE, QUICKED_UNIMPLEMENTED, QUICKED_WIP = -3, -4, -10, 1
+QB200_ERR_NO_DEVICE, QB200_ERR_CUDA, QB200_ERR_ARG, QB200_ERR_OOM, QB200_ERR_CAPACITY = -100, -101, -102, -103, -104
+
+# every symbol the two headers declare (tests/test_cabi.py checks the library exports all of them)
+EXPORTS = ["quicked_check_error", "quicked_status_msg", "quicked_default_params", "quicked_new", "quicked_free",
+           "quicked_align", "qb200_device_count", "qb200_create", "qb200_destroy", "qb200_set_stream",
+           "qb200_set_workspace_limit", "qb200_last_error", "qb200_upload", "qb200_upload_device", "qb200_run",
+           "qb200_download", "qb200_get_stats", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
+           "qb200_generate_pairs"]
+
+
+class Params(C.Structure):        # quicked_params_t, 48 bytes
+    _fields_ = [("algo", C.c_int), ("bandwidth", C.c_uint), ("window_size", C.c_uint), ("overlap_size", C.c_uint),
+                ("hew_threshold", C.c_uint * 2), ("hew_percentage", C.c_uint * 2), ("only_score", C.c_bool),
+                ("force_scalar", C.c_bool), ("external_timer", C.c_bool), ("external_allocator", C.c_void_p)]
+
+
+class Aligner(C.Structure):       # quicked_aligner_t, 72 bytes
+    _fields_ = [("params", C.POINTER(Params)), ("mm_allocator", C.c_void_p), ("cigar", C.c_char_p), ("score", C.c_int),
+                ("timer", C.c_void_p), ("timer_windowed_s", C.c_void_p), ("timer_windowed_l", C.c_void_p),
+                ("timer_banded", C.c_void_p), ("timer_align", C.c_void_p)]
+
+
+class Batch(C.Structure):         # qb200_batch_t
+    _fields_ = [("seqs", C.c_void_p), ("seqs_bytes", C.c_int64), ("n_pairs", C.c_int64), ("pattern_off", C.c_void_p),
+                ("pattern_len", C.c_void_p), ("text_off", C.c_void_p), ("text_len", C.c_void_p)]
+
+
+class Results(C.Structure):       # qb200_results_t
+    _fields_ = [("score", C.c_void_p), ("status", C.c_void_p), ("cigar", C.c_void_p), ("cigar_capacity", C.c_int64),
+                ("cigar_off", C.c_void_p), ("cigar_bytes", C.c_int64)]
+
+
+class Stats(C.Structure):         # qb200_stats_t
+    _fields_ = [(k, C.c_int64) for k in ("n_pairs", "kernel_launches", "word_steps", "word_steps_windowed",
+                                         "word_steps_banded", "cells", "h2d_bytes", "d2h_bytes", "pairs_stage2",
+                                         "pairs_stage3", "banded_tries", "hirschberg_splits", "leaves")] + \
+               [(k, C.c_float) for k in ("ms_total", "ms_prepare", "ms_windowed_s", "ms_windowed_l", "ms_banded",
+                                         "ms_align_fill", "ms_align_trace", "ms_cigar")] + [("matrix_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """Load libquicked_b200.so (built in-tree by quicked_b200/build.py).  No fallback: raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m quicked_b200.build` (nvcc, sm_100a). "
+                          "There is no CPU fallback for the QuickEd GPU path.")
+    L = C.CDLL(LIB_PATH)
+    L.quicked_default_params.restype = Params
+    L.quicked_new.argtypes = [C.POINTER(Aligner), C.POINTER(Params)]
+    L.quicked_free.argtypes = [C.POINTER(Aligner)]
+    L.quicked_align.argtypes = [C.POINTER(Aligner), C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    L.quicked_status_msg.restype = C.c_char_p
+    L.quicked_status_msg.argtypes = [C.c_int]
+    L.quicked_check_error.restype = C.c_bool
+    L.quicked_check_error.argtypes = [C.c_int]
+    L.qb200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.qb200_destroy.argtypes = [C.c_void_p]
+    L.qb200_destroy.restype = None
+    L.qb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.qb200_set_workspace_limit.argtypes = [C.c_void_p, C.c_size_t]
+    L.qb200_last_error.restype = C.c_char_p
+    L.qb200_last_error.argtypes = [C.c_void_p]
+    for f in ("qb200_upload", "qb200_upload_device"):
+        getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Batch)]
+    L.qb200_run.argtypes = [C.c_void_p, C.POINTER(Params)]
+    L.qb200_download.argtypes = [C.c_void_p, C.POINTER(Results)]
+    L.qb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.qb200_align_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Batch), C.POINTER(Results)]
+    L.qb200_host_alloc.restype = C.c_void_p
+    L.qb200_host_alloc.argtypes = [C.c_size_t]
+    L.qb200_host_free.argtypes = [C.c_void_p]
+    L.qb200_host_free.restype = None
+    L.qb200_generate_pairs.restype = C.c_int64
+    L.qb200_generate_pairs.argtypes = [C.c_uint64, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]
+    _lib = L
+    return L
+
+
+class QuickedException(Exception):
+    def __init__(self, status):
+        self.status = status
+        super().__init__(load().quicked_status_msg(status).decode().strip())
+
+
+def make_params(**kw):
+    p = load().quicked_default_params()
+    for k, v in kw.items():
+        if k in ("hew_threshold", "hew_percentage"):
+            if isinstance(v, int):
+                v = (v, v)
+            getattr(p, k)[0], getattr(p, k)[1] = v
+        else:
+            setattr(p, k, v)
+    return p
+
+
+class QuickedAligner:
+    """Single-pair aligner with the reference binding's interface (bindings/cpp/quicked.hpp:46-73)."""
+
+    def __init__(self):
+        self._lib = load()
+        self._params = self._lib.quicked_default_params()
+        self._aligner = Aligner()
+        st = self._lib.quicked_new(C.byref(self._aligner), C.byref(self._params))
+        if self._lib.quicked_check_error(st):
+            raise QuickedException(st)
+
+    def __del__(self):
+        try:
+            self._lib.quicked_free(C.byref(self._aligner))
+        except Exception:
+            pass
+
+    def align(self, pattern, text):
+        pattern = pattern.encode() if isinstance(pattern, str) else bytes(pattern)
+        text = text.encode() if isinstance(text, str) else bytes(text)
+        st = self._lib.quicked_align(C.byref(self._aligner), pattern, len(pattern), text, len(text))
+        self.status = st
+        if self._lib.quicked_check_error(st):
+            raise QuickedException(st)
+        return st
+
+    def setAlgorithm(self, algo): self._params.algo = int(algo)
+    def setOnlyScore(self, v): self._params.only_score = bool(v)
+    def setBandwidth(self, v): self._params.bandwidth = int(v)
+    def setWindowSize(self, v): self._params.window_size = int(v)
+    def setOverlapSize(self, v): self._params.overlap_size = int(v)
+    def setForceScalar(self, v): self._params.force_scalar = bool(v)
+    def setHEWThreshold(self, v): self._params.hew_threshold[0] = self._params.hew_threshold[1] = int(v)
+    def setHEWPercentage(self, v): self._params.hew_percentage[0] = self._params.hew_percentage[1] = int(v)
+    def getScore(self): return self._aligner.score
+    def getCigar(self): return self._aligner.cigar.decode() if self._aligner.cigar else "NULL"
+
+
+def pack_pairs(pairs):
+    """[(pattern, text), ...] -> (seqs uint8[...], pattern_off, pattern_len, text_off, text_len) numpy arrays,
+    the packed layout of qb200_batch_t (pattern i then text i, back to back)."""
+    n = len(pairs)
+    po = np.zeros(n, np.int64); to = np.zeros(n, np.int64)
+    pl = np.zeros(n, np.int32); tl = np.zeros(n, np.int32)
+    chunks, off = [], 0
+    for i, (p, t) in enumerate(pairs):
+        p = p.encode() if isinstance(p, str) else bytes(p)
+        t = t.encode() if isinstance(t, str) else bytes(t)
+        po[i], pl[i] = off, len(p); off += len(p)
+        to[i], tl[i] = off, len(t); off += len(t)
+        chunks.append(p); chunks.append(t)
+    seqs = np.frombuffer(b"".join(chunks) + b"\0", dtype=np.uint8).copy()
+    return seqs, po, pl, to, tl
+
+
+class BatchAligner:
+    """One GPU context (device buffers, stream).  align(pairs) -> (status[], score[], [cigar str])."""
+
+    def __init__(self, device=0, stream=None, workspace_limit=None):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.qb200_create(C.byref(h), int(device))
+        if rc == QB200_ERR_NO_DEVICE:
+            raise RuntimeError("quicked_b200: no CUDA device — the GPU path has no CPU fallback")
+        if rc != 0:
+            raise RuntimeError(f"qb200_create failed rc={rc}")
+        self._h = h
+        if stream is not None:
+            self._lib.qb200_set_stream(self._h, C.c_void_p(int(stream)))
+        if workspace_limit:
+            self._lib.qb200_set_workspace_limit(self._h, int(workspace_limit))
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed rc={rc}: {self._lib.qb200_last_error(self._h).decode()}")
+
+    @staticmethod
+    def _batch(seqs_ptr, seqs_bytes, n, po, pl, to, tl):
+        return Batch(seqs_ptr, seqs_bytes, n, po, pl, to, tl)
+
+    def upload_arrays(self, seqs, po, pl, to, tl):
+        """numpy (host) arrays in the packed layout"""
+        self._keep = (seqs, po, pl, to, tl)
+        b = self._batch(seqs.ctypes.data, int(seqs.size), int(po.size), po.ctypes.data, pl.ctypes.data, to.ctypes.data,
+                        tl.ctypes.data)
+        self._n = int(po.size)
+        self._check(self._lib.qb200_upload(self._h, C.byref(b)), "qb200_upload")
+
+    def upload_device_ptrs(self, seqs_ptr, seqs_bytes, n, po_ptr, pl_ptr, to_ptr, tl_ptr):
+        """device pointers (e.g. torch tensors' data_ptr()); the character buffer is used in place"""
+        b = self._batch(seqs_ptr, seqs_bytes, n, po_ptr, pl_ptr, to_ptr, tl_ptr)
+        self._n = int(n)
+        self._check(self._lib.qb200_upload_device(self._h, C.byref(b)), "qb200_upload_device")
+
+    def run(self, params=None, **kw):
+        p = params if params is not None else make_params(**kw)
+        self._check(self._lib.qb200_run(self._h, C.byref(p)), "qb200_run")
+
+    def download(self, want_cigar=True):
+        n = self._n
+        score = np.empty(n, np.int32); status = np.empty(n, np.int32)
+        off = np.zeros(n + 1, np.int64)
+        r = Results(score.ctypes.data, status.ctypes.data, None, 0, off.ctypes.data, 0)
+        rc = self._lib.qb200_download(self._h, C.byref(r))
+        cig = None
+        if rc == QB200_ERR_CAPACITY and want_cigar:
+            cig = np.empty(int(r.cigar_bytes), np.uint8)
+            r = Results(score.ctypes.data, status.ctypes.data, cig.ctypes.data, int(cig.size), off.ctypes.data, 0)
+            rc = self._lib.qb200_download(self._h, C.byref(r))
+        if rc not in (0, QB200_ERR_CAPACITY):
+            self._check(rc, "qb200_download")
+        return status, score, off, cig
+
+    def stats(self):
+        s = Stats()
+        self._lib.qb200_get_stats(self._h, C.byref(s))
+        return s.as_dict()
+
+    def align(self, pairs, params=None, **kw):
+        """-> list of (status, score, cigar-or-None), same tuple shape as the oracle harness"""
+        self.upload_arrays(*pack_pairs(pairs))
+        self.run(params, **kw)
+        status, score, off, cig = self.download()
+        out = []
+        raw = cig.tobytes() if cig is not None else b""
+        for i in range(len(pairs)):
+            c = None
+            if cig is not None and off[i + 1] - off[i] > 1:
+                c = raw[off[i]:off[i + 1] - 1].decode()
+            out.append((int(status[i]), int(score[i]), c))
+        return out
+
+
+def generate_pairs_native(seed, n_pairs, length, error):
+    """Seeded generate_dataset twin in C (qb200_generate_pairs).  -> (seqs, po, pl, to, tl) numpy arrays."""
+    import math
+    L = load()
+    nerr = int(error) if error >= 1.0 else int(math.ceil(np.float32(length) * np.float32(error)))
+    stride = 2 * length + nerr + 2
+    total = (n_pairs * stride + 15) // 16 * 16
+    seqs = np.zeros(total, np.uint8)
+    po = np.zeros(n_pairs, np.int64); to = np.zeros(n_pairs, np.int64)
+    pl = np.zeros(n_pairs, np.int32); tl = np.zeros(n_pairs, np.int32)
+    rc = L.qb200_generate_pairs(seed, n_pairs, length, float(error), seqs.ctypes.data, po.ctypes.data, pl.ctypes.data,
+                                to.ctypes.data, tl.ctypes.data)
+    if rc < 0:
+        raise RuntimeError(f"qb200_generate_pairs rc={rc}")
+    return seqs, po, pl, to, tl

@@ -1,0 +1,194 @@
+// qb_banded.cuh — BandEd: banded bit-parallel (Myers) edit distance with the reference's sliding, self-cutting band.
+//
+// k_banded_warp<R, FULL>: ONE TASK PER WARP, one 64-row block per lane (R blocks per lane for bands up to 32*R
+// blocks).  All lanes work on the SAME text column, so the match-mask fetch is a conflict-free broadcast-indexed
+// LDS and the band bookkeeping is warp-uniform.  The vertical dependency between the blocks of a column is
+//   (a) the 64-bit adder carry of Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq crossing block boundaries, and
+//   (b) bit 63 of Ph / Mh shifting into bit 0 of the next block.
+// The reference resolves it serially, block after block (bpm_banded.c:238-261: PHin/MHin = previous PHout/MHout,
+// with MHin folded into Eq).  Here (a) is resolved for all 32 lanes at once by a carry-lookahead over two ballots
+// (generate = local add overflowed, propagate = local sum is all ones): the adder carry into a block equals the
+// reference's MHin of that block (carry-out of bit 63 of (Eq&Pv)+Pv is Pv63 & Xh63 = Mh63), and (b) is one more
+// ballot of Ph bit 63.  The update is therefore bit-identical to BPM_ADVANCE_BLOCK (bpm_commons.h:49-68) on every
+// block of the pattern.
+//
+// Between two band shifts (64 columns) a lane owns fixed blocks, so Pv/Mv/score stay in registers; shared memory
+// is only the re-mapping medium at the shift (slots indexed by absolute block, so the reference's "move every word
+// down by one" (bpm_banded.c:279-287 / :902-910) costs nothing) and holds the lane's 5 match masks of the block.
+//
+// FULL=false: score-only pass up to column `finish` (reference bpm_banded.c:791-964 == AVX2 :349-788); exports the
+//             final column (Pv, Mv per band word), per-block scores and lower/higher block for Hirschberg.
+// FULL=true : every column is stored for the traceback (reference bpm_banded.c:199-316), as 16-byte (Pv,Mv)
+//             entries [column][band word] — one coalesced 512-byte store per warp-column.
+#pragma once
+#include "qb_common.cuh"
+
+namespace qb {
+
+template <int R>
+struct BandedSmem {
+    static constexpr int kCap = 32 * R + 2;                       // slots (absolute block mod kCap)
+    static constexpr int kBytesPerWarp = kCap * 16 + R * kAlpha * 32 * 8 + 64;
+};
+
+template <int R, bool FULL>
+__global__ void __launch_bounds__(128)
+k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ codes,
+              const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix, int *__restrict__ scores_pool,
+              u64 *__restrict__ state_pool, BandOut *__restrict__ outs, u64 *__restrict__ counters)
+{
+    constexpr int kCap = BandedSmem<R>::kCap;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int task_id = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (task_id >= n_tasks) return;
+    unsigned char *base = smem_raw + (size_t)wib * BandedSmem<R>::kBytesPerWarp;
+    u64 *s_pv = reinterpret_cast<u64 *>(base);
+    u64 *s_mv = s_pv + kCap;
+    u64 *s_eq = s_mv + kCap;                                        // [R][5][32]
+    unsigned char *s_txt = reinterpret_cast<unsigned char *>(s_eq + R * kAlpha * 32);
+
+    const BandTask tk = tasks[task_id];
+    const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+    const int B = (int)(FULL ? g.Bc : g.Bs);
+    const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63;
+    const int clamp = FULL ? nblk - 1 : nblk;                       // bpm_banded.c:295 vs :917
+    const int prolog = (int)g.prolog;
+    const i64 fin = g.fin, kcut = g.k;
+    const u64 *pq = peq + tk.peq_off;
+    int *scores = scores_pool + tk.scores_off;
+    const unsigned char *tcodes = codes + tk.t_off;
+    const int ncols = FULL ? tk.n : tk.finish;
+
+    int first = prolog, last = B - 1, pos_v = -prolog, pos_h = 0;  // bpm_banded.c:222-225
+    // ---- reset (bpm_banded.c:180-197): Pv = ~0, Mv = 0, scores[i] = 64(i+1) ----
+    for (int j = lane; j < B; j += 32) {
+        scores[j] = 64 * (j + 1);
+        const int blk = j + pos_v;
+        if (blk >= 0) { s_pv[blk % kCap] = ~0ull; s_mv[blk % kCap] = 0ull; }
+        if (FULL) matrix[tk.mat_off + j] = make_ulonglong2(~0ull, 0ull);
+    }
+    __syncwarp();
+
+    u64 ws = 0;
+    u64 pv[R], mv[R];
+    int sc[R], ob[R];
+    for (int col0 = 0; col0 < ncols; col0 += 64) {
+        const int nc = min(64, ncols - col0);
+        // ---- load the 64 columns' codes and this lane's blocks ----
+        for (int c = lane; c < 64; c += 32) {
+            const int col = col0 + c;
+            unsigned char code = 4;
+            if (col < tk.n) code = tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col];
+            s_txt[c] = code;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = first + 32 * r + lane;
+            const bool act = j <= last;
+            const int blk = j + pos_v;
+            pv[r] = act ? s_pv[blk % kCap] : 0ull;
+            mv[r] = act ? s_mv[blk % kCap] : 0ull;
+            sc[r] = act ? scores[blk] : 0;
+            ob[r] = (blk == nblk - 1 && mmod) ? mmod - 1 : 63;      // level_mask, bpm_banded.c:88-102
+#pragma unroll
+            for (int c = 0; c < kAlpha; ++c)
+                s_eq[(r * kAlpha + c) * 32 + lane] = act ? pq[(i64)c * tk.nbp + blk] : 0ull;
+        }
+        __syncwarp();
+        const int live = last - first + 1;
+        // ---- the column loop ----
+        for (int c = 0; c < nc; ++c) {
+            const int code = s_txt[c];
+            u32 cin = 0, hp_carry = 1;                               // top of the band: PHin = 1, MHin = 0 (:238)
+            const bool store_col = FULL && !(c == 63);               // the 64th column is stored after the shift
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int j = first + 32 * r + lane;
+                const bool act = j <= last;
+                const u64 eq = s_eq[(r * kAlpha + code) * 32 + lane];
+                const u64 a = eq & pv[r];
+                const u64 s = a + pv[r];
+                const u32 G = __ballot_sync(kFull, act && (s < a));
+                const u32 P = __ballot_sync(kFull, act && (s == ~0ull));
+                const u32 X = G | P;
+                const u64 sum = (u64)X + (u64)G + (u64)cin;
+                const u32 carries = (u32)sum ^ X ^ G;                // bit l = carry into lane l
+                const u32 my_c = (carries >> lane) & 1u;             // == the reference's MHin of this block
+                const u64 xh = ((s + my_c) ^ pv[r]) | eq;
+                u64 ph = mv[r] | ~(xh | pv[r]);
+                u64 mh = pv[r] & xh;
+                const u32 HP = __ballot_sync(kFull, (ph >> 63) != 0);
+                const u32 hp_in = lane ? ((HP >> (lane - 1)) & 1u) : hp_carry;
+                sc[r] += (int)((ph >> ob[r]) & 1ull) - (int)((mh >> ob[r]) & 1ull);   // :260
+                ph = (ph << 1) | (u64)hp_in;
+                mh = (mh << 1) | (u64)my_c;
+                const u64 xv = eq | mv[r];
+                pv[r] = mh | ~(xv | ph);
+                mv[r] = ph & xv;
+                if (store_col && act)
+                    matrix[tk.mat_off + (i64)(col0 + c + 1) * B + j] = make_ulonglong2(pv[r], mv[r]);
+                cin = (u32)(sum >> 32);
+                hp_carry = HP >> 31;
+            }
+        }
+        ws += (u64)live * nc;
+        // ---- write the lane's blocks back ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int j = first + 32 * r + lane;
+            if (j <= last) {
+                const int blk = j + pos_v;
+                s_pv[blk % kCap] = pv[r]; s_mv[blk % kCap] = mv[r];
+                scores[blk] = sc[r];
+            }
+        }
+        __syncwarp();
+        if (nc < 64) break;                                          // tail columns: no shift (:925-951)
+        // ---- end of a 64-column block (bpm_banded.c:264-301 / :889-922), warp-uniform ----
+        {
+            const bool cut_lo = (first + 2 < last) && (fin > 64 * (i64)(first + 1)) &&
+                                ((i64)scores[first + pos_v + 1] + (fin - 64 * (i64)(first + 1)) > kcut);
+            if (cut_lo && pos_h >= prolog) ++first;
+            else if (!cut_lo && pos_h < prolog) --first;
+            const int nb = last + pos_v + 1;                          // the block entering at the bottom
+            __syncwarp();
+            if (lane == 0) {
+                s_pv[nb % kCap] = ~0ull; s_mv[nb % kCap] = 0ull;
+                scores[nb] = scores[nb - 1] + 64;
+            }
+            __syncwarp();
+            if (FULL) {    // column col0+64 is stored in the coordinates of the next block of columns (:279-287)
+                for (int j = first + lane; j <= last; j += 32) {
+                    const int blk = j + pos_v + 1;
+                    matrix[tk.mat_off + (i64)(col0 + 64) * B + j] = make_ulonglong2(s_pv[blk % kCap], s_mv[blk % kCap]);
+                }
+            }
+            const bool cut_hi = (first + 2 < last) && (64 * (i64)(last - 1) > fin) &&
+                                ((i64)scores[last + pos_v - 1] + (64 * (i64)(last - 1) - fin) > kcut);
+            if (cut_hi || (pos_v + last >= clamp)) --last;
+            ++pos_v; ++pos_h;
+        }
+        __syncwarp();
+    }
+    // ---- results ----
+    if (!FULL) {
+        u64 *st = state_pool + tk.state_off;                         // Pv[B] then Mv[B], band-relative
+        for (int j = lane; j < B; j += 32) {
+            const int blk = j + pos_v;
+            const bool act = (j >= first && j <= last && blk >= 0);
+            st[j] = act ? s_pv[blk % kCap] : 0ull;
+            st[B + j] = act ? s_mv[blk % kCap] : 0ull;
+        }
+    }
+    if (lane == 0) {
+        BandOut o;
+        const int sfin = scores[nblk - 1];                            // bpm_banded.c:952-961
+        o.score = mmod ? sfin - (64 - mmod) : sfin;
+        o.first = first; o.last = last; o.pos_v = pos_v;
+        outs[tk.slot] = o;
+        atomicAdd(&counters[1], ws);
+    }
+}
+
+}  // namespace qb

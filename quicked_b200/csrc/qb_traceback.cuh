@@ -1,0 +1,129 @@
+// qb_traceback.cuh — BandEd traceback (reference bpm_banded.c:967-1036) and CIGAR text emission
+// (reference cigar.c:453-488 "%d%c" run-length text with matches printed, cigar.c:274-289 edit score).
+//
+// The walk reproduces the reference's tie-breaking exactly: from (v,h) = (m-1,n-1),
+//   D if bit v of Pv[column h+1];  else I if bit v of Mv[column h];  else M / X by RAW byte compare;
+// leftovers become I... then D....  Column c of the stored matrix holds the state after c text columns in the band
+// coordinates of column block c/64.
+//
+// Ops are emitted right-to-left as 2-bit codes packed 16 per u32 into the tail of the task's op region (the
+// reference writes one char per op into a right-aligned buffer, cigar.h:33-47).  While walking we also count the
+// edit cost and the byte length of the run-length text, so single-leaf pairs need no second pass over the ops.
+#pragma once
+#include "qb_common.cuh"
+
+namespace qb {
+
+struct OpWriter {
+    u32 *words;     // op region of the task
+    int pos;        // next op goes to pos-1
+    u32 acc;
+    int cost, text_len, cur_op, cur_len;
+    __device__ __forceinline__ void init(u32 *w, int cap) { words = w; pos = cap; acc = 0; cost = 0; text_len = 0; cur_op = -1; cur_len = 0; }
+    __device__ __forceinline__ void emit(int op)
+    {
+        --pos;
+        acc |= (u32)op << (2 * (pos & 15));
+        if ((pos & 15) == 0) { words[pos >> 4] = acc; acc = 0; }
+        cost += (op != OP_M);
+        if (op == cur_op) ++cur_len;
+        else {
+            if (cur_len) text_len += dec_digits((unsigned)cur_len) + 1;
+            cur_op = op; cur_len = 1;
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (pos & 15) words[pos >> 4] = acc;
+        if (cur_len) text_len += dec_digits((unsigned)cur_len) + 1;
+    }
+};
+
+// One leaf per thread: simple pointer-chasing walk over the [column][band word] matrix written by k_banded_warp<.,true>.
+__global__ void __launch_bounds__(128)
+k_traceback_thread(const BandTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ raw,
+                   const ulonglong2 *__restrict__ matrix, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_tasks) return;
+    const BandTask tk = tasks[id];
+    const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+    const int B = (int)g.Bc, prolog = (int)g.prolog;
+    const ulonglong2 *mat = matrix + tk.mat_off;
+    const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
+    OpWriter w; w.init(ops_pool + tk.ops_off, tk.ops_cap);
+    int h = tk.n - 1, v = tk.m - 1;
+    while (v >= 0 && h >= 0) {
+        const int ev = v - 64 * ((h >> 6) - prolog);
+        const int evr = v - 64 * (((h + 1) >> 6) - prolog);
+        const int wr = evr >> 6, wl = ev >> 6;
+        u64 pvw = 0, mvw = 0;
+        if (wr >= 0 && wr < B) pvw = mat[(i64)(h + 1) * B + wr].x;
+        if (wl >= 0 && wl < B) mvw = mat[(i64)h * B + wl].y;
+        if ((pvw >> (evr & 63)) & 1ull) { w.emit(OP_D); --v; }
+        else if ((mvw >> (ev & 63)) & 1ull) { w.emit(OP_I); --h; }
+        else { w.emit(traw[h] == praw[v] ? OP_M : OP_X); --h; --v; }
+    }
+    while (h >= 0) { w.emit(OP_I); --h; }
+    while (v >= 0) { w.emit(OP_D); --v; }
+    w.finish();
+    LeafOut o;
+    o.n_ops = tk.ops_cap - w.pos; o.cost = w.cost; o.text_len = w.text_len;
+    o.first_op = w.cur_op; o.first_run = w.cur_len;
+    outs[tk.slot] = o;
+}
+
+// Per-pair list of leaves (left to right).  Single-leaf pairs: n_leaves == 1.
+struct PairLeaves {
+    i64 first_leaf;   // index into the global leaf arrays (BandTask / LeafOut), leaves of a pair are contiguous
+    int n_leaves;
+    int pad_;
+};
+
+__device__ __forceinline__ int put_run(char *dst, int len, int op)
+{
+    const int nd = dec_digits((unsigned)len);
+    unsigned x = (unsigned)len;
+    for (int k = nd - 1; k >= 0; --k) { dst[k] = (char)('0' + x % 10u); x /= 10u; }
+    dst[nd] = "MXID"[op];
+    return nd + 1;
+}
+
+// Pass over a pair's ops, merging runs across leaf boundaries.  WRITE=false: only measure (text bytes without NUL,
+// and the edit cost); WRITE=true: write the text at cigar + cigar_off[pair] and NUL-terminate.
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_cigar_text(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask *__restrict__ leaves,
+             const LeafOut *__restrict__ leaf_out, const u32 *__restrict__ ops_pool, int *__restrict__ text_len,
+             const i64 *__restrict__ cigar_off, char *__restrict__ cigar)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const PairLeaves p = pl[i];
+    char *dst = WRITE ? cigar + cigar_off[i] : nullptr;
+    int out = 0, cur_op = -1, cur_len = 0;
+    for (int l = 0; l < p.n_leaves; ++l) {
+        const BandTask tk = leaves[p.first_leaf + l];
+        const int n_ops = leaf_out[p.first_leaf + l].n_ops;
+        const u32 *words = ops_pool + tk.ops_off;
+        int pos = tk.ops_cap - n_ops;
+        const int end = tk.ops_cap;
+        while (pos < end) {
+            const u32 wv = words[pos >> 4];
+            const int stop = min(end, (pos | 15) + 1);
+            for (; pos < stop; ++pos) {
+                const int op = (wv >> (2 * (pos & 15))) & 3;
+                if (op == cur_op) ++cur_len;
+                else {
+                    if (cur_len) out += WRITE ? put_run(dst + out, cur_len, cur_op) : dec_digits((unsigned)cur_len) + 1;
+                    cur_op = op; cur_len = 1;
+                }
+            }
+        }
+    }
+    if (cur_len) out += WRITE ? put_run(dst + out, cur_len, cur_op) : dec_digits((unsigned)cur_len) + 1;
+    if (WRITE) dst[out] = 0;
+    else text_len[i] = out;
+}
+
+}  // namespace qb

@@ -1,0 +1,104 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C-ABI
+(libquicked_b200.so via quicked_b200.capi) and is compared bit-exactly with the CPU oracle on the same
+seeded inputs, and with the committed golden vectors dumped from the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+
+from quicked_b200.datagen import generate_pairs
+from _common import GOLDEN, expand_rle, golden_kw, load_golden, replay, sha
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from quicked_b200 import BatchAligner, load
+    lib = load()
+    assert lib.qb200_device_count() > 0, "no CUDA device visible: the GPU tests cannot run"
+    a = BatchAligner(device=0)
+    yield a
+    a.close()
+
+
+def check_against_oracle(gpu, oracle, pairs, allow_unimplemented=False, **kw):
+    got = gpu.align(pairs, **kw)
+    n_checked = 0
+    for (p, t), g in zip(pairs, got):
+        if allow_unimplemented and g[0] == -10:
+            continue
+        exp = oracle.align(p, t, **kw)
+        assert g == exp, (kw, len(p), len(t), g[:2], exp[:2])
+        n_checked += 1
+    return n_checked
+
+
+@pytest.mark.parametrize("length,error,num", [(100, 0.05, 400), (1000, 0.10, 200), (300, 0.25, 100), (3000, 0.2, 40),
+                                              (10000, 0.2, 16), (64, 0.1, 64), (130, 0.02, 64)])
+def test_quicked_matches_oracle(gpu, oracle, length, error, num):
+    pairs = generate_pairs(num, length, error, seed=2000 + length)
+    assert check_against_oracle(gpu, oracle, pairs, algo=0) == num
+    assert check_against_oracle(gpu, oracle, pairs, algo=0, force_scalar=True) == num
+
+
+@pytest.mark.parametrize("bandwidth", [5, 15, 20, 40])
+def test_banded_matches_oracle(gpu, oracle, bandwidth):
+    for length, error, num in [(100, 0.05, 100), (1000, 0.1, 60), (10000, 0.2, 8)]:
+        pairs = generate_pairs(num, length, error, seed=3000 + length)
+        check_against_oracle(gpu, oracle, pairs, algo=2, bandwidth=bandwidth)
+
+
+def test_hirschberg_no_split_matches_oracle(gpu, oracle):
+    for length, error, num in [(100, 0.05, 100), (1000, 0.1, 60), (10000, 0.2, 8)]:
+        pairs = generate_pairs(num, length, error, seed=4000 + length)
+        check_against_oracle(gpu, oracle, pairs, algo=3, bandwidth=20)
+
+
+def test_known_answers(gpu):
+    got = gpu.align([("GATC", "GATO"), ("ACGT", "ACTT"), ("", ""), ("ACGT", ""), ("A", "A")])
+    assert got[0][:2] == (1, 1)
+    assert got[1] == (1, 1, "2M1X1M")
+    assert got[2][0] == -4 and got[3][0] == -4
+    assert got[4] == (1, 0, "1M")
+    assert all(g[0] == -3 for g in gpu.align([("ACGT", "ACGT")], algo=9))
+
+
+def test_golden_explicit(gpu):
+    gold = load_golden("golden_explicit.json")
+    pairs = [(c["pattern"], c["text"]) for c in gold["cases"]]
+    for aname in ("quicked", "banded", "hirschberg", "banded_5"):
+        got = gpu.align(pairs, **golden_kw(gold, aname))
+        for c, g in zip(gold["cases"], got):
+            if aname in c["out"] and g[0] != -10:
+                e = c["out"][aname]
+                assert g == (e["status"], e["score"], e["cigar"]), (aname, c["pattern"], c["text"])
+
+
+@pytest.mark.parametrize("set_idx", [0, 1, 2, 6])
+def test_golden_seeded(gpu, set_idx):
+    gold = load_golden("golden_seeded.json")
+    s = gold["sets"][set_idx]
+    pairs = generate_pairs(s["num"], s["length"], s["error"], seed=s["seed"], indels=tuple(s["indels"]) if s["indels"] else None)
+    for aname in ("quicked", "banded", "hirschberg", "banded_5"):
+        got = gpu.align(pairs, **golden_kw(gold, aname))
+        for g, exp in zip(got, s["out"][aname]):
+            if exp is None or g[0] == -10:
+                continue
+            assert [g[0], g[1], sha(g[2])] == exp, (s["name"], aname)
+
+
+def test_cigars_replay_and_ragged(gpu, oracle):
+    rng = np.random.default_rng(7)
+    pairs = []
+    for _ in range(200):
+        m = int(rng.integers(1, 600)); n = max(1, m + int(rng.integers(-30, 31)))
+        pairs.append((bytes(rng.choice(list(b"ACGTN"), size=m).astype(np.uint8)),
+                      bytes(rng.choice(list(b"ACGTNacgt"), size=n).astype(np.uint8))))
+    for algo in (0, 2, 3):
+        got = gpu.align(pairs, algo=algo, bandwidth=30)
+        for (p, t), g in zip(pairs, got):
+            if g[0] == -10:
+                continue
+            assert g == oracle.align(p, t, algo=algo, bandwidth=30)
+            assert replay(expand_rle(g[2]), p.decode(), t.decode()) == g[1]

@@ -35,7 +35,8 @@ template <int R, bool FULL>
 __global__ void __launch_bounds__(128)
 k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ codes,
               const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix, int *__restrict__ scores_pool,
-              u64 *__restrict__ state_pool, BandOut *__restrict__ outs, u64 *__restrict__ counters)
+              u64 *__restrict__ state_pool, int2 *__restrict__ range_pool, BandOut *__restrict__ outs,
+              u64 *__restrict__ counters)
 {
     constexpr int kCap = BandedSmem<R>::kCap;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -61,6 +62,10 @@ k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned ch
     const int ncols = FULL ? tk.n : tk.finish;
 
     int first = prolog, last = B - 1, pos_v = -prolog, pos_h = 0;  // bpm_banded.c:222-225
+    // FULL: live range of every 64-column block, so the traceback can treat never-written cells as 0 (what a fresh
+    // arena holds in the reference) instead of reading stale pool memory
+    int2 *ranges = FULL ? range_pool + tk.range_off : nullptr;
+    if (FULL && lane == 0) ranges[0] = make_int2(first, last);
     // ---- reset (bpm_banded.c:180-197): Pv = ~0, Mv = 0, scores[i] = 64(i+1) ----
     for (int j = lane; j < B; j += 32) {
         scores[j] = 64 * (j + 1);
@@ -149,6 +154,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned ch
         {
             const bool cut_lo = (first + 2 < last) && (fin > 64 * (i64)(first + 1)) &&
                                 ((i64)scores[first + pos_v + 1] + (fin - 64 * (i64)(first + 1)) > kcut);
+            const int first_old = first;
             if (cut_lo && pos_h >= prolog) ++first;
             else if (!cut_lo && pos_h < prolog) --first;
             const int nb = last + pos_v + 1;                          // the block entering at the bottom
@@ -159,6 +165,12 @@ k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned ch
             }
             __syncwarp();
             if (FULL) {    // column col0+64 is stored in the coordinates of the next block of columns (:279-287)
+                // when the top block is cut, the reference's in-place shift leaves the pre-shift word at index
+                // first_old; a too-narrow band can make the traceback read it, so keep it identical
+                if (first > first_old && lane == 0) {
+                    const int blk = first_old + pos_v;
+                    matrix[tk.mat_off + (i64)(col0 + 64) * B + first_old] = make_ulonglong2(s_pv[blk % kCap], s_mv[blk % kCap]);
+                }
                 for (int j = first + lane; j <= last; j += 32) {
                     const int blk = j + pos_v + 1;
                     matrix[tk.mat_off + (i64)(col0 + 64) * B + j] = make_ulonglong2(s_pv[blk % kCap], s_mv[blk % kCap]);
@@ -168,6 +180,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned ch
                                 ((i64)scores[last + pos_v - 1] + (64 * (i64)(last - 1) - fin) > kcut);
             if (cut_hi || (pos_v + last >= clamp)) --last;
             ++pos_v; ++pos_h;
+            if (FULL && lane == 0) ranges[pos_h] = make_int2(first, last);
         }
         __syncwarp();
     }

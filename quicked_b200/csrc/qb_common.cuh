@@ -41,6 +41,7 @@ struct BandTask {
     i64 scores_off;       // int32 index: per-block running scores (zero-initialised)
     i64 state_off;        // score-only: u64 index where the final Pv[B] then Mv[B] are exported
     i64 ops_off;          // leaf: u32 index of the 2-bit op words region
+    i64 range_off;        // leaf: int2 index of the per-column-block live range (first,last) of the band
     int ops_cap;          // leaf: capacity in ops (= m+n rounded up to 16)
     int slot;             // free for the scheduler (e.g. node id in the Hirschberg tree)
 };

@@ -70,7 +70,7 @@ struct qb200_ctx {
     DevBuf d_raw, d_codes, d_pairs, d_peq, d_peqjobs;
     // per-run
     DevBuf d_bound, d_hew, d_score, d_status, d_textlen, d_cigoff, d_cigar, d_counters, d_scan_tmp;
-    DevBuf d_leaves, d_leafout, d_pairleaves, d_work, d_bandout, d_matrix, d_scores, d_state, d_ops;
+    DevBuf d_leaves, d_leafout, d_pairleaves, d_work, d_bandout, d_matrix, d_scores, d_state, d_ops, d_ranges;
     std::vector<int> h_score, h_status;
     std::vector<i64> h_cigoff_;
     i64 cigar_total = 0;
@@ -166,7 +166,7 @@ int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, int n_tasks)
     const int blocks = (n_tasks + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, ctx->stream>>>(d_tasks, n_tasks, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
                                                    ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(),
-                                                   ctx->d_state.as<u64>(), ctx->d_bandout.as<BandOut>(),
+                                                   ctx->d_state.as<u64>(), ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(),
                                                    ctx->d_counters.as<u64>());
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
@@ -227,7 +227,7 @@ int run_leaves(qb200_ctx *ctx, std::vector<BandTask> &h_leaves)
     size_t i0 = 0;
     std::vector<BandTask> work;
     while (i0 < nl) {
-        i64 ent = 0, sc = 0;
+        i64 ent = 0, sc = 0, rg = 0;
         size_t i1 = i0;
         while (i1 < nl && (i1 == i0 || ent + mat_entries[i1] <= limit_entries)) { ent += mat_entries[i1]; sc += score_ints[i1]; ++i1; }
         if (ent > limit_entries && i1 == i0 + 1 && (size_t)ent * 16 > free_b + ctx->d_matrix.cap) {
@@ -237,7 +237,10 @@ int run_leaves(qb200_ctx *ctx, std::vector<BandTask> &h_leaves)
         work.clear();
         work.reserve(i1 - i0);
         i64 mo = 0, so = 0;
-        for (size_t i = i0; i < i1; ++i) { h_leaves[i].mat_off = mo; h_leaves[i].scores_off = so; mo += mat_entries[i]; so += score_ints[i]; }
+        for (size_t i = i0; i < i1; ++i) {
+            h_leaves[i].mat_off = mo; h_leaves[i].scores_off = so; h_leaves[i].range_off = rg;
+            mo += mat_entries[i]; so += score_ints[i]; rg += h_leaves[i].n / 64 + 2;
+        }
         int group_begin[7] = {0}, gi = 0;
         const int Rs[6] = {1, 2, 4, 8, 16, 32};
         for (int r = 0; r < 6; ++r) {
@@ -247,6 +250,7 @@ int run_leaves(qb200_ctx *ctx, std::vector<BandTask> &h_leaves)
         group_begin[6] = (int)work.size();
         CK(ctx->d_matrix.reserve((size_t)ent * 16));
         CK(ctx->d_scores.reserve((size_t)sc * 4 + 16));
+        CK(ctx->d_ranges.reserve((size_t)rg * 8 + 16));
         CK(ctx->d_work.reserve(sizeof(BandTask) * work.size()));
         CK(cudaMemcpyAsync(ctx->d_work.p, work.data(), sizeof(BandTask) * work.size(), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)sc * 4, ctx->stream));
@@ -262,8 +266,8 @@ int run_leaves(qb200_ctx *ctx, std::vector<BandTask> &h_leaves)
             Span sp(ctx, ST_TRACE);
             const int nt = (int)work.size();
             k_traceback_thread<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_work.as<BandTask>(), nt, ctx->raw(),
-                                                                          ctx->d_matrix.as<ulonglong2>(), ctx->d_ops.as<u32>(),
-                                                                          ctx->d_leafout.as<LeafOut>());
+                                                                          ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(),
+                                                                          ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>());
             CK(cudaGetLastError());
             ctx->stats.kernel_launches++;
         }
@@ -334,7 +338,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
     for (DevBuf *b : {&ctx->d_raw, &ctx->d_codes, &ctx->d_pairs, &ctx->d_peq, &ctx->d_peqjobs, &ctx->d_bound, &ctx->d_hew,
                       &ctx->d_score, &ctx->d_status, &ctx->d_textlen, &ctx->d_cigoff, &ctx->d_cigar, &ctx->d_counters,
                       &ctx->d_scan_tmp, &ctx->d_leaves, &ctx->d_leafout, &ctx->d_pairleaves, &ctx->d_work, &ctx->d_bandout,
-                      &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops})
+                      &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges})
         b->release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

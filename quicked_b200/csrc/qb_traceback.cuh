@@ -39,10 +39,25 @@ struct OpWriter {
     }
 };
 
+// Was band word `w` of stored column `c` ever written by the fill?  Column c (state after c text columns) was written
+// with the live range of column block (c-1)/64; a column with c%64==0 is stored after the shift, i.e. with the next
+// block's first and the previous block's last (bpm_banded.c:279-287).  Never-written cells read as 0, which is what
+// the reference finds there when its arena is fresh (and what the oracle defines).
+__device__ __forceinline__ bool cell_written(const int2 *ranges, int B, int c, int w)
+{
+    if (w < 0 || w >= B) return false;
+    if (c == 0) return true;
+    const int kb = (c - 1) >> 6;
+    const int2 r = ranges[kb];
+    const int lo = (c & 63) ? r.x : min(r.x, ranges[kb + 1].x);   // a cut top word keeps its pre-shift value
+    return w >= lo && w <= r.y;
+}
+
 // One leaf per thread: simple pointer-chasing walk over the [column][band word] matrix written by k_banded_warp<.,true>.
 __global__ void __launch_bounds__(128)
 k_traceback_thread(const BandTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ raw,
-                   const ulonglong2 *__restrict__ matrix, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
+                   const ulonglong2 *__restrict__ matrix, const int2 *__restrict__ range_pool,
+                   u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_tasks) return;
@@ -50,6 +65,7 @@ k_traceback_thread(const BandTask *__restrict__ tasks, int n_tasks, const unsign
     const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
     const int B = (int)g.Bc, prolog = (int)g.prolog;
     const ulonglong2 *mat = matrix + tk.mat_off;
+    const int2 *ranges = range_pool + tk.range_off;
     const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
     OpWriter w; w.init(ops_pool + tk.ops_off, tk.ops_cap);
     int h = tk.n - 1, v = tk.m - 1;
@@ -58,8 +74,8 @@ k_traceback_thread(const BandTask *__restrict__ tasks, int n_tasks, const unsign
         const int evr = v - 64 * (((h + 1) >> 6) - prolog);
         const int wr = evr >> 6, wl = ev >> 6;
         u64 pvw = 0, mvw = 0;
-        if (wr >= 0 && wr < B) pvw = mat[(i64)(h + 1) * B + wr].x;
-        if (wl >= 0 && wl < B) mvw = mat[(i64)h * B + wl].y;
+        if (cell_written(ranges, B, h + 1, wr)) pvw = mat[(i64)(h + 1) * B + wr].x;
+        if (cell_written(ranges, B, h, wl)) mvw = mat[(i64)h * B + wl].y;
         if ((pvw >> (evr & 63)) & 1ull) { w.emit(OP_D); --v; }
         else if ((mvw >> (ev & 63)) & 1ull) { w.emit(OP_I); --h; }
         else { w.emit(traw[h] == praw[v] ? OP_M : OP_X); --h; --v; }

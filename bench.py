@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native QuickEd bound-and-align path.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation on the host cores
+
+A "step" is one pass of the hot path (QUICKED: WindowEd bound -> BandEd/Hirschberg alignment -> score + CIGAR)
+over one batch of synthetic pairs.  The default workload is BASELINE.json configs[1]: 1 kbp pairs at 10 % error,
+1 M pairs per GPU (weak scaling: every rank aligns its own contiguous index range; there is no collective on the
+data path, only the barrier + max-over-ranks of the timing).
+
+  value : alignments/s, whole job, inputs already resident in HBM when the timed region starts (kernel path only)
+  e2e   : the same metric through qb200_align_batch() with HOST buffers — pinned-host ASCII in, host scores +
+          CIGAR text out, both copies inside the timed region
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {   # name: (length, error, pairs per GPU, description)
+    "c1": (100, 0.05, 100000, "generate_dataset 100 bp pairs at 5% error, 100k pairs"),
+    "c2": (1000, 0.10, 1000000, "generate_dataset 1 kbp pairs at 10% error, 1M pairs, QuickEd score + CIGAR"),
+    "c3": (10000, 0.20, 100000, "generate_dataset 10 kbp pairs at 20% error, 100k pairs, score + CIGAR"),
+    "c4": (100000, 0.20, 2048, "generate_dataset 100 kbp pairs at 20% error, 2048 pairs, Hirschberg CIGAR"),
+}
+ALGOS = {"quicked": 0, "windowed": 1, "banded": 2, "hirschberg": 3}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(length, error, algo_kw, sample_pairs, seed, threads=None):
+    """Time the reference's CPU implementation (oracle/_ref when built, else the oracle port) on `sample_pairs`
+    pairs of the workload with all host threads.  -> (pairs/s, cores, kind, seconds)"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import harness
+    import quicked_b200 as qb
+    seqs, po, pl, to, tl = qb.generate_pairs_native(seed, sample_pairs, length, error)
+    raw = seqs.tobytes()
+    pairs = [(raw[po[i]:po[i] + pl[i]], raw[to[i]:to[i] + tl[i]]) for i in range(sample_pairs)]
+    kind = "reference" if harness.Reference.available() else "port"
+    threads = threads or os.cpu_count() or 1
+    threads = max(1, min(threads, sample_pairs))
+
+    def work(chunk):
+        impl = harness.Reference() if kind == "reference" else harness.Oracle()   # one handle per thread (ctypes releases the GIL)
+        s = 0
+        for p, t in chunk:
+            s += impl.align(p, t, **algo_kw)[1]
+        return s
+
+    chunks = [pairs[i::threads] for i in range(threads)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, chunks))
+    dt = time.perf_counter() - t0
+    return sample_pairs / dt, threads, kind, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default="quicked", choices=sorted(ALGOS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's)")
+    ap.add_argument("--bandwidth", type=int, default=20)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto, ~10-30 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    length, error, n_pairs, desc = WORKLOADS[args.workload]
+    if args.pairs:
+        n_pairs = args.pairs
+    algo_kw = {"algo": ALGOS[args.algo]}
+    if args.algo in ("banded", "hirschberg"):
+        algo_kw["bandwidth"] = args.bandwidth
+    metric, unit = "alignments_per_second", "alignments/s"
+    config = {"workload": f"{args.workload}: {desc}", "algo": args.algo, "pairs_per_gpu": n_pairs, "length": length,
+              "error": error, "score_and_cigar": True, "l2": "inputs_exceed_l2", "sharding": f"contiguous index ranges x{world}, no collective"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # ~600 us/pair-thread at 10 kbp, ~50 us at 1 kbp, ~6 us at 100 bp: size each step for a few seconds
+        per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000}[args.workload]
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or int(max(cores, min(n_pairs, 4e6 * cores / per_pair_us)))
+        vals = []
+        for s in range(args.warmup + args.steps):
+            if s < args.warmup and s > 0:
+                continue          # one warm-up pass is enough for a CPU loop
+            v, used, kind, dt = cpu_reference_arm(length, error, algo_kw, sample, seed=99 + s)
+            if s >= args.warmup:
+                vals.append((v, dt))
+        v = sum(sample for _ in vals) / sum(dt for _, dt in vals)
+        ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
+        out = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u64", "data": "synthetic", "config": config,
+               "cpu_baseline": {"value": v, "unit": unit, "cores": used, "kind": kind,
+                                "sample": f"{sample} pairs of the workload per step, {used} host threads"},
+               "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gcups_equiv": v * length * length / 1e9}
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    import quicked_b200 as qb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the QuickEd GPU path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # rank r aligns the contiguous index range [r*n_pairs, (r+1)*n_pairs) of the (virtual) job
+    seqs, po, pl, to, tl = qb.generate_pairs_native(1000 + rank, n_pairs, length, error)
+    lib = qb.load()
+    # pinned host staging for the end-to-end leg
+    import ctypes as C
+    pin = lib.qb200_host_alloc(seqs.size)
+    pinned = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint8)), shape=(seqs.size,))
+    pinned[:] = seqs
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu = qb.BatchAligner(device=local_rank, stream=stream)
+    params = qb.make_params(**algo_kw)
+
+    # ---- kernel path, inputs resident in HBM ----
+    gpu.upload_arrays(pinned, po, pl, to, tl)
+    for _ in range(args.warmup):
+        gpu.run(params)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    stage = {}
+    launches = 0
+    for _ in range(args.steps):
+        gpu.run(params)
+        st = gpu.stats()
+        launches += st["kernel_launches"]
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage[k] = stage.get(k, 0.0) + v
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / args.steps
+    value = world * n_pairs / (ms_step * 1e-3)
+    st = gpu.stats()
+    status, score, off, cig = gpu.download()
+    ok_frac = float((status >= 0).mean())
+
+    # ---- end to end through the C-ABI with host buffers (H2D + kernels + D2H inside the timed region) ----
+    score_h = np.empty(n_pairs, np.int32); status_h = np.empty(n_pairs, np.int32); off_h = np.zeros(n_pairs + 1, np.int64)
+    cig_cap = int(cig.size * 1.05) + 4096 if cig is not None else 16
+    cpin = lib.qb200_host_alloc(cig_cap)
+    batch = qb.capi.Batch(pinned.ctypes.data, int(pinned.size), n_pairs, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data)
+    res = qb.capi.Results(score_h.ctypes.data, status_h.ctypes.data, cpin, cig_cap, off_h.ctypes.data, 0)
+
+    def e2e_step():
+        rc = lib.qb200_align_batch(gpu._h, C.byref(params), C.byref(batch), C.byref(res))
+        if rc != 0:
+            raise RuntimeError(f"qb200_align_batch rc={rc}: {lib.qb200_last_error(gpu._h).decode()}")
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * n_pairs * args.steps / dt
+    st_e = gpu.stats()
+    assert np.array_equal(score_h, score), "end-to-end scores differ from the resident run"
+
+    # ---- roofline of the dominant kernel ----
+    peaks, peak_kind = measured_peaks()
+    stage_avg = {k: v / args.steps for k, v in stage.items() if k != "ms_total"}
+    dom = max(stage_avg, key=stage_avg.get) if stage_avg else None
+    int_peak = gpu.int_peak_tops()
+    # the traceback-state fill: every word-step writes its 16-byte (Pv,Mv) entry (SURVEY §8d "spilled-matrix": 16 B/word-step)
+    fill_ms = stage_avg.get("ms_align_fill", 0.0)
+    fill_bytes = 16.0 * st["word_steps_banded"]
+    roof = None
+    if fill_ms > 0:
+        ach = fill_bytes / (fill_ms * 1e-3) / 1e9
+        roof = {"kernel": "k_banded_thread/k_banded_warp (BandEd full-matrix fill)", "bound": "hbm", "achieved": ach,
+                "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": ach / peaks.get("hbm_gbs"), "traffic": None,
+                "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs", "algorithmic_bytes_per_word_step": 16,
+                "ms_per_launch": fill_ms}
+    int_roof = {"achieved_tops": 24.0 * st["word_steps"] / (ms_step * 1e-3) / 1e12, "peak_tops": int_peak,
+                "frac": 24.0 * st["word_steps"] / (ms_step * 1e-3) / 1e12 / int_peak if int_peak else None,
+                "ops_per_word_step": 24, "word_steps_per_step": st["word_steps"],
+                "peak_source": "qb200_measure_int_peak (LOP3+IADD3 microbenchmark, this run)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000}[args.workload]
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or int(max(cores, min(n_pairs, 15e6 * cores / per_pair_us)))
+        v, used, kind, cdt = cpu_reference_arm(length, error, algo_kw, sample, seed=1000)
+        cpu = {"value": v, "unit": unit, "cores": used, "kind": kind,
+               "sample": f"{sample} pairs of the workload, {used} host threads, {cdt:.1f} s"}
+
+    if rank == 0:
+        out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+               "data": "synthetic", "config": config,
+               "gcups_equiv": value * length * length / 1e9,
+               "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(st_e["h2d_bytes"]),
+                       "d2h_bytes_per_step": int(st_e["d2h_bytes"])},
+               "gpu_launches": int(launches), "roofline": roof, "int_alu_roofline": int_roof, "cpu_baseline": cpu,
+               "clocks": clocks, "stage_ms_per_step": stage_avg, "dominant_stage": dom,
+               "pairs_ok_fraction": ok_frac, "mean_score": float(score.mean())}
+        print(json.dumps(out))
+    lib.qb200_host_free(pin); lib.qb200_host_free(cpin)
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

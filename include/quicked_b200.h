@@ -88,6 +88,10 @@ int qb200_get_stats(qb200_ctx_t *ctx, qb200_stats_t *stats);
 int qb200_align_batch(qb200_ctx_t *ctx, const quicked_params_t *params,
                       const qb200_batch_t *host_batch, qb200_results_t *host_results);
 
+/* --- measured integer-ALU peak (LOP3+IADD3 mix, no memory traffic), in 10^12 int32 ops/s: the denominator of the
+ * bit-op roofline (MEASURED_PEAKS.json carries only HBM and bf16 peaks) --- */
+int qb200_measure_int_peak(qb200_ctx_t *ctx, double *tera_ops_per_s);
+
 /* --- pinned host staging helpers (cudaHostAlloc / cudaFreeHost) --- */
 void *qb200_host_alloc(size_t bytes);
 void  qb200_host_free(void *p);

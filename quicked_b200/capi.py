@@ -26,7 +26,7 @@ EXPORTS = ["quicked_check_error", "quicked_status_msg", "quicked_default_params"
            "quicked_align", "qb200_device_count", "qb200_create", "qb200_destroy", "qb200_set_stream",
            "qb200_set_workspace_limit", "qb200_last_error", "qb200_upload", "qb200_upload_device", "qb200_run",
            "qb200_download", "qb200_get_stats", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
-           "qb200_generate_pairs"]
+           "qb200_generate_pairs", "qb200_measure_int_peak"]
 
 
 class Params(C.Structure):        # quicked_params_t, 48 bytes
@@ -95,6 +95,7 @@ def load():
     L.qb200_download.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.qb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.qb200_align_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Batch), C.POINTER(Results)]
+    L.qb200_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qb200_host_alloc.restype = C.c_void_p
     L.qb200_host_alloc.argtypes = [C.c_size_t]
     L.qb200_host_free.argtypes = [C.c_void_p]
@@ -248,6 +249,11 @@ class BatchAligner:
         if rc not in (0, QB200_ERR_CAPACITY):
             self._check(rc, "qb200_download")
         return status, score, off, cig
+
+    def int_peak_tops(self):
+        v = C.c_double()
+        self._check(self._lib.qb200_measure_int_peak(self._h, C.byref(v)), "qb200_measure_int_peak")
+        return v.value
 
     def stats(self):
         s = Stats()

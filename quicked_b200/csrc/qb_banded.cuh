@@ -33,10 +33,10 @@ struct BandedSmem {
 
 template <int R, bool FULL>
 __global__ void __launch_bounds__(128)
-k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ codes,
-              const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix, int *__restrict__ scores_pool,
-              u64 *__restrict__ state_pool, int2 *__restrict__ range_pool, BandOut *__restrict__ outs,
-              u64 *__restrict__ counters)
+k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
+              const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
+              int *__restrict__ scores_pool, u64 *__restrict__ state_pool, int2 *__restrict__ range_pool,
+              BandOut *__restrict__ outs, u64 *__restrict__ counters)
 {
     constexpr int kCap = BandedSmem<R>::kCap;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -49,9 +49,14 @@ k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned ch
     u64 *s_eq = s_mv + kCap;                                        // [R][5][32]
     unsigned char *s_txt = reinterpret_cast<unsigned char *>(s_eq + R * kAlpha * 32);
 
-    const BandTask tk = tasks[task_id];
+    BandTask tk = tasks[list ? list[begin + task_id] : begin + task_id];
+    tk.mat_off -= mat_sub;
     const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
     const int B = (int)(FULL ? g.Bc : g.Bs);
+    {   // tasks of other band heights are handled by the launch of their own R (one list, one launch per R)
+        const int need = B <= 32 ? 1 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : 32;
+        if (need != R) return;
+    }
     const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63;
     const int clamp = FULL ? nblk - 1 : nblk;                       // bpm_banded.c:295 vs :917
     const int prolog = (int)g.prolog;
@@ -71,7 +76,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned ch
         scores[j] = 64 * (j + 1);
         const int blk = j + pos_v;
         if (blk >= 0) { s_pv[blk % kCap] = ~0ull; s_mv[blk % kCap] = 0ull; }
-        if (FULL) matrix[tk.mat_off + j] = make_ulonglong2(~0ull, 0ull);
+        if (FULL) matrix[tk.mat_off + j] = make_ulonglong2(~0ull, 0ull);   // warp layout: mat_cs == B, mat_ws == 1
     }
     __syncwarp();
 
@@ -202,6 +207,115 @@ k_banded_warp(const BandTask *__restrict__ tasks, int n_tasks, const unsigned ch
         outs[tk.slot] = o;
         atomicAdd(&counters[1], ws);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_banded_thread<BMAX>: full-matrix BandEd for NARROW bands (B_cigar <= BMAX blocks), ONE LEAF PER THREAD.
+//
+// At 100 bp - 1 kbp and <= 10 % error the band is 3 blocks tall: a warp-per-pair mapping would idle 29 lanes, so
+// here each thread carries its whole band (Pv, Mv, running scores) in registers and walks the blocks of a column
+// serially exactly like the reference's inner loop (bpm_banded.c:238-261) — no cross-lane traffic at all.
+// The 32 leaves of a warp are interleaved in the matrix: entry (column c, band word w, lane l) lives at
+// group_base + (c*Bg + w)*32 + l, so every (Pv,Mv) store of the warp is one coalesced 512-byte line group.
+// The lane's 5 match masks per live block are staged in shared memory ([slot][thread], conflict-free) once per
+// 64 columns; the per-column fetch is an LDS indexed by the column's code.
+template <int BMAX>
+__global__ void __launch_bounds__(128)
+k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
+                const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
+                int2 *__restrict__ range_pool, u64 *__restrict__ counters)
+{
+    extern __shared__ u64 s_eq_all[];                       // [BMAX*5][blockDim.x]
+    const int T = blockDim.x, tid = threadIdx.x;
+    u64 *s_eq = s_eq_all + tid;
+    const int id = blockIdx.x * T + tid;
+    u64 ws = 0;
+    if (id < n_tasks) {
+        BandTask tk = tasks[list ? list[begin + id] : begin + id];
+        tk.mat_off -= mat_sub;
+        const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+        const int B = (int)g.Bc, prolog = (int)g.prolog;
+        const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63, clamp = nblk - 1;
+        const i64 fin = g.fin, kcut = g.k;
+        const u64 *pq = peq + tk.peq_off;
+        const unsigned char *tcodes = codes + tk.t_off;
+        ulonglong2 *mat = matrix + tk.mat_off;
+        const i64 cs = tk.mat_cs, wsd = tk.mat_ws;
+        int2 *ranges = range_pool + tk.range_off;
+        int first = prolog, last = B - 1, pos_v = -prolog, pos_h = 0;
+        u64 pv[BMAX], mv[BMAX];
+        int sc[BMAX];
+#pragma unroll
+        for (int j = 0; j < BMAX; ++j) {
+            pv[j] = ~0ull; mv[j] = 0ull; sc[j] = 64 * (j + pos_v + 1);            // scores[blk] = 64(blk+1)
+            if (j < B) mat[j * wsd] = make_ulonglong2(~0ull, 0ull);               // column 0
+        }
+        ranges[0] = make_int2(first, last);
+        for (int col0 = 0; col0 < tk.n; col0 += 64) {
+            const int nc = min(64, tk.n - col0);
+            int ob[BMAX];
+#pragma unroll
+            for (int j = 0; j < BMAX; ++j) {
+                const int blk = j + pos_v;
+                ob[j] = (blk == nblk - 1 && mmod) ? mmod - 1 : 63;
+                if (j >= first && j <= last) {
+#pragma unroll
+                    for (int c = 0; c < kAlpha; ++c)
+                        s_eq[(j * kAlpha + c) * T] = (blk < tk.nbp) ? pq[(i64)c * tk.nbp + blk] : 0ull;
+                }
+            }
+            for (int c = 0; c < nc; ++c) {
+                const int code = tk.rev ? tcodes[tk.n - 1 - (col0 + c)] : tcodes[col0 + c];
+                ulonglong2 *dst = mat + (i64)(col0 + c + 1) * cs;
+                u32 hp = 1, hm = 0;
+#pragma unroll
+                for (int j = 0; j < BMAX; ++j) {
+                    if (j >= first && j <= last) {
+                        u32 hpo, hmo;
+                        myers_step_at(s_eq[(j * kAlpha + code) * T], pv[j], mv[j], hp, hm, ob[j], hpo, hmo);
+                        sc[j] += (int)hpo - (int)hmo;
+                        hp = hpo; hm = hmo;
+                        dst[j * wsd] = make_ulonglong2(pv[j], mv[j]);
+                    }
+                }
+            }
+            ws += (u64)max(last - first + 1, 0) * nc;
+            if (nc < 64) break;
+            // ---- end of a 64-column block (bpm_banded.c:264-301) ----
+            int s_f1 = 0, s_l1 = 0, s_l = 0;            // scores[first+1], scores[last-1], scores[last] (band-relative)
+#pragma unroll
+            for (int j = 0; j < BMAX; ++j) {
+                if (j == first + 1) s_f1 = sc[j];
+                if (j == last - 1) s_l1 = sc[j];
+                if (j == last) s_l = sc[j];
+            }
+            const bool cut_lo = (first + 2 < last) && (fin > 64 * (i64)(first + 1)) && ((i64)s_f1 + (fin - 64 * (i64)(first + 1)) > kcut);
+            if (cut_lo && pos_h >= prolog) ++first;
+            else if (!cut_lo && pos_h < prolog) --first;
+            // shift every word up by one band index; the block entering at the bottom starts at Pv = ~0, Mv = 0
+#pragma unroll
+            for (int j = 0; j < BMAX - 1; ++j) { pv[j] = pv[j + 1]; mv[j] = mv[j + 1]; sc[j] = sc[j + 1]; }
+#pragma unroll
+            for (int j = 0; j < BMAX; ++j)
+                if (j == last) { pv[j] = ~0ull; mv[j] = 0ull; sc[j] = s_l + 64; }
+            // column col0+64 re-stored in the next block's coordinates (the pre-shift store above stays underneath,
+            // exactly like the reference's in-place shift, bpm_banded.c:279-287)
+            {
+                ulonglong2 *dst = mat + (i64)(col0 + 64) * cs;
+#pragma unroll
+                for (int j = 0; j < BMAX; ++j)
+                    if (j >= first && j <= last) dst[j * wsd] = make_ulonglong2(pv[j], mv[j]);
+            }
+            // scores[last-1] in the OLD coordinates is sc[last-2] after the shift; s_l1 was read before it
+            const bool cut_hi = (first + 2 < last) && (64 * (i64)(last - 1) > fin) && ((i64)s_l1 + (64 * (i64)(last - 1) - fin) > kcut);
+            if (cut_hi || (pos_v + last >= clamp)) --last;
+            ++pos_v; ++pos_h;
+            ranges[pos_h] = make_int2(first, last);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ws += __shfl_down_sync(kFull, ws, o);
+    if ((tid & 31) == 0 && ws) atomicAdd(&counters[1], ws);
 }
 
 }  // namespace qb

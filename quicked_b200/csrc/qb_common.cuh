@@ -38,6 +38,7 @@ struct BandTask {
     int nbp;
     int pair;             // owning pair index
     i64 mat_off;          // full mode: first 16-byte (Pv,Mv) entry of this task in the matrix pool
+    int mat_cs, mat_ws;   // full mode: entry (column c, band word w) lives at mat_off + c*mat_cs + w*mat_ws
     i64 scores_off;       // int32 index: per-block running scores (zero-initialised)
     i64 state_off;        // score-only: u64 index where the final Pv[B] then Mv[B] are exported
     i64 ops_off;          // leaf: u32 index of the 2-bit op words region

@@ -14,8 +14,11 @@
 #include <vector>
 
 #include "../../include/quicked_b200.h"
+#include <cub/device/device_scan.cuh>
+
 #include "qb_banded.cuh"
 #include "qb_common.cuh"
+#include "qb_plan.cuh"
 #include "qb_prep.cuh"
 #include "qb_traceback.cuh"
 #include "qb_windowed.cuh"
@@ -50,7 +53,7 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum Stage { ST_PREP = 0, ST_WS, ST_WL, ST_BANDED, ST_FILL, ST_TRACE, ST_CIGAR, ST_COUNT };
+enum Stage { ST_PREP = 0, ST_WS, ST_WL, ST_BANDED, ST_FILL, ST_TRACE, ST_CIGAR, ST_PLAN, ST_COUNT };
 
 }  // namespace
 
@@ -71,6 +74,9 @@ struct qb200_ctx {
     // per-run
     DevBuf d_bound, d_hew, d_score, d_status, d_textlen, d_cigoff, d_cigar, d_counters, d_scan_tmp;
     DevBuf d_leaves, d_leafout, d_pairleaves, d_work, d_bandout, d_matrix, d_scores, d_state, d_ops, d_ranges;
+    DevBuf d_cls, d_cutoff, d_plan_items, d_plan_offs, d_textbytes, d_list_t, d_list_w, d_list_slow, d_gsize, d_goff, d_gB;
+    unsigned char *h_pinned = nullptr;     // small pinned mailbox for totals
+    bool unknown_algo = false, multi_leaf_pairs = false;
     std::vector<int> h_score, h_status;
     std::vector<i64> h_cigoff_;
     i64 cigar_total = 0;
@@ -93,6 +99,30 @@ struct qb200_ctx {
             return e_ == cudaErrorMemoryAllocation ? QB200_ERR_OOM : QB200_ERR_CUDA;                  \
         }                                                                                             \
     } while (0)
+
+
+// ---- integer-ALU peak microbenchmark (roofline denominator for the bit-op work; MEASURED_PEAKS.json has none) ----
+// 8 independent chains per thread of LOP3 + IADD (the instruction mix of a Myers block update), no memory traffic.
+__global__ void __launch_bounds__(256) k_int_peak(u32 *out, int iters, u32 a, u32 b, u32 c)
+{
+    u32 x[8], y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = threadIdx.x * 2654435761u + i * a; y[i] = blockIdx.x + i * b; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                x[i] = ((x[i] & a) | y[i]) ^ c;      // one LOP3
+                y[i] = y[i] + x[i];                   // one IADD3
+            }
+        }
+    }
+    u32 r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= x[i] + y[i];
+    if (r == 0x12345678u) out[0] = r;
+}
 
 namespace {
 
@@ -155,7 +185,7 @@ int finish_upload(qb200_ctx *ctx)
 }
 
 template <int R, bool FULL>
-int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, int n_tasks)
+int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub)
 {
     if (n_tasks <= 0) return 0;
     const int bpw = BandedSmem<R>::kBytesPerWarp;
@@ -164,8 +194,8 @@ int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, int n_tasks)
     auto kern = k_banded_warp<R, FULL>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (n_tasks + wpb - 1) / wpb;
-    kern<<<blocks, wpb * 32, smem, ctx->stream>>>(d_tasks, n_tasks, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
-                                                   ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(),
+    kern<<<blocks, wpb * 32, smem, ctx->stream>>>(d_tasks, d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(),
+                                                   ctx->d_peq.as<u64>(), ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(),
                                                    ctx->d_state.as<u64>(), ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(),
                                                    ctx->d_counters.as<u64>());
     CK(cudaGetLastError());
@@ -179,128 +209,73 @@ int rounds_for(i64 B)
     return 0;
 }
 
+// One launch per band-height class present in the list (each warp exits at once if its task belongs to another class).
 template <bool FULL>
-int launch_banded(qb200_ctx *ctx, int R, const BandTask *d_tasks, int n_tasks)
+int launch_banded(qb200_ctx *ctx, unsigned r_mask, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub)
 {
-    switch (R) {
-    case 1: return launch_banded_r<1, FULL>(ctx, d_tasks, n_tasks);
-    case 2: return launch_banded_r<2, FULL>(ctx, d_tasks, n_tasks);
-    case 4: return launch_banded_r<4, FULL>(ctx, d_tasks, n_tasks);
-    case 8: return launch_banded_r<8, FULL>(ctx, d_tasks, n_tasks);
-    case 16: return launch_banded_r<16, FULL>(ctx, d_tasks, n_tasks);
-    case 32: return launch_banded_r<32, FULL>(ctx, d_tasks, n_tasks);
-    }
-    ctx->err = "band too tall for the implemented kernels";
-    return QB200_ERR_ARG;
+    int rc = 0;
+    if (!rc && (r_mask & 1)) rc = launch_banded_r<1, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
+    if (!rc && (r_mask & 2)) rc = launch_banded_r<2, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
+    if (!rc && (r_mask & 4)) rc = launch_banded_r<4, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
+    if (!rc && (r_mask & 8)) rc = launch_banded_r<8, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
+    if (!rc && (r_mask & 16)) rc = launch_banded_r<16, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
+    if (!rc && (r_mask & 32)) rc = launch_banded_r<32, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
+    return rc;
 }
 
-// ---- leaves: BandEd full matrix + traceback for a list of tasks (pair order), chunked by the matrix pool ----
-// h_leaves[i].slot must equal i.  On return d_leaves / d_leafout hold all leaves and their results.
-int run_leaves(qb200_ctx *ctx, std::vector<BandTask> &h_leaves)
-{
-    const size_t nl = h_leaves.size();
-    if (!nl) return 0;
-    // op regions + per-task geometry
-    i64 ops_words = 0;
-    std::vector<int> rounds(nl);
-    std::vector<i64> mat_entries(nl), score_ints(nl);
-    for (size_t i = 0; i < nl; ++i) {
-        BandTask &t = h_leaves[i];
-        const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
-        rounds[i] = rounds_for(g.Bc);
-        if (!rounds[i]) { ctx->err = "leaf band of " + std::to_string(g.Bc) + " blocks exceeds 1024"; return QB200_ERR_ARG; }
-        mat_entries[i] = (i64)(t.n + 1) * g.Bc;
-        score_ints[i] = (i64)((t.m + 63) / 64) + g.Bc + 2;
-        t.ops_cap = ((t.m + t.n + 15) / 16) * 16;
-        t.ops_off = ops_words;
-        ops_words += t.ops_cap / 16;
-        t.slot = (int)i;
-    }
-    CK(ctx->d_ops.reserve((size_t)ops_words * 4 + 16));
-    CK(ctx->d_leaves.reserve(sizeof(BandTask) * nl));
-    CK(ctx->d_leafout.reserve(sizeof(LeafOut) * nl));
-    CK(ctx->d_bandout.reserve(sizeof(BandOut) * nl));
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    const i64 limit_entries = (i64)(std::min<size_t>(ctx->matrix_limit, (size_t)((free_b + ctx->d_matrix.cap) * 0.85)) / 16);
+constexpr int kThreadBandMax = 4;
 
-    size_t i0 = 0;
-    std::vector<BandTask> work;
-    while (i0 < nl) {
-        i64 ent = 0, sc = 0, rg = 0;
-        size_t i1 = i0;
-        while (i1 < nl && (i1 == i0 || ent + mat_entries[i1] <= limit_entries)) { ent += mat_entries[i1]; sc += score_ints[i1]; ++i1; }
-        if (ent > limit_entries && i1 == i0 + 1 && (size_t)ent * 16 > free_b + ctx->d_matrix.cap) {
-            ctx->err = "a single traceback matrix does not fit the device"; return QB200_ERR_OOM;
-        }
-        // assign pool offsets, group by rounds
-        work.clear();
-        work.reserve(i1 - i0);
-        i64 mo = 0, so = 0;
-        for (size_t i = i0; i < i1; ++i) {
-            h_leaves[i].mat_off = mo; h_leaves[i].scores_off = so; h_leaves[i].range_off = rg;
-            mo += mat_entries[i]; so += score_ints[i]; rg += h_leaves[i].n / 64 + 2;
-        }
-        int group_begin[7] = {0}, gi = 0;
-        const int Rs[6] = {1, 2, 4, 8, 16, 32};
-        for (int r = 0; r < 6; ++r) {
-            group_begin[gi++] = (int)work.size();
-            for (size_t i = i0; i < i1; ++i) if (rounds[i] == Rs[r]) work.push_back(h_leaves[i]);
-        }
-        group_begin[6] = (int)work.size();
-        CK(ctx->d_matrix.reserve((size_t)ent * 16));
-        CK(ctx->d_scores.reserve((size_t)sc * 4 + 16));
-        CK(ctx->d_ranges.reserve((size_t)rg * 8 + 16));
-        CK(ctx->d_work.reserve(sizeof(BandTask) * work.size()));
-        CK(cudaMemcpyAsync(ctx->d_work.p, work.data(), sizeof(BandTask) * work.size(), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)sc * 4, ctx->stream));
-        {
-            Span sp(ctx, ST_FILL);
-            for (int r = 0; r < 6; ++r) {
-                const int nb = group_begin[r + 1] - group_begin[r];
-                int rc = launch_banded<true>(ctx, Rs[r], ctx->d_work.as<BandTask>() + group_begin[r], nb);
-                if (rc) return rc;
-            }
-        }
-        {
-            Span sp(ctx, ST_TRACE);
-            const int nt = (int)work.size();
-            k_traceback_thread<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_work.as<BandTask>(), nt, ctx->raw(),
-                                                                          ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(),
-                                                                          ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>());
-            CK(cudaGetLastError());
-            ctx->stats.kernel_launches++;
-        }
-        ctx->stats.matrix_bytes += ent * 16;
-        // the work list is reused by the next chunk: wait for this one (also bounds the pool lifetime)
-        CK(cudaStreamSynchronize(ctx->stream));
-        i0 = i1;
-    }
-    ctx->stats.leaves += (i64)nl;
-    CK(cudaMemcpyAsync(ctx->d_leaves.p, h_leaves.data(), sizeof(BandTask) * nl, cudaMemcpyHostToDevice, ctx->stream));
+int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub)
+{
+    if (n_tasks <= 0) return 0;
+    const int T = 128;
+    const size_t smem = (size_t)kThreadBandMax * kAlpha * T * 8;
+    k_banded_thread<kThreadBandMax><<<(n_tasks + T - 1) / T, T, smem, ctx->stream>>>(
+        ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
+        ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(), ctx->d_counters.as<u64>());
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
     return 0;
 }
 
-// ---- CIGAR text + scores for pairs whose leaves are done ----
-int emit_results(qb200_ctx *ctx, const std::vector<PairLeaves> &h_pl, bool want_cigar)
+int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub)
 {
-    const i64 n = ctx->n_pairs;
-    Span sp(ctx, ST_CIGAR);
-    CK(ctx->d_pairleaves.reserve(sizeof(PairLeaves) * (size_t)n));
-    CK(cudaMemcpyAsync(ctx->d_pairleaves.p, h_pl.data(), sizeof(PairLeaves) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    const int blocks = (int)((n + 127) / 128);
-    // pass 1: text bytes per pair (also needed for the offsets when only the score is wanted: cheap, skip then)
-    CK(ctx->d_textlen.reserve((size_t)(n + 1) * 4));
-    CK(ctx->d_cigoff.reserve((size_t)(n + 1) * 8));
-    if (want_cigar) {
-        k_cigar_text<false><<<blocks, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), (int)n, ctx->d_leaves.as<BandTask>(),
-                                                             ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), ctx->d_textlen.as<int>(),
-                                                             nullptr, nullptr);
-        CK(cudaGetLastError());
-        ctx->stats.kernel_launches++;
-    }
+    if (n_tasks <= 0) return 0;
+    k_traceback_thread<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub,
+                                                                        ctx->raw(), ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(),
+                                                                        ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>());
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
     return 0;
 }
+
+// Largest e in (s, n] such that the entries of items s..e-1 fit `limit` (at least one item).  One thread, binary search.
+__global__ void k_chunk_end_groups(const i64 *goff, const i64 *gsize, int n, int s, i64 limit, int *out)
+{
+    int lo = s + 1, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (goff[mid - 1] + gsize[mid - 1] - goff[s] <= limit) lo = mid; else hi = mid - 1;
+    }
+    out[0] = lo;
+}
+__global__ void k_chunk_end_leaves(const BandTask *leaves, const int *list, int n, int s, i64 limit, int *out, i64 *start_off)
+{
+    const i64 base = leaves[list[s]].mat_off;
+    int lo = s + 1, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        const BandTask &t = leaves[list[mid - 1]];
+        if (t.mat_off + (i64)(t.n + 1) * t.mat_cs - base <= limit) lo = mid; else hi = mid - 1;
+    }
+    out[0] = lo; start_off[0] = base;
+}
+
+struct RunPlan {
+    PlanSum tot;          // totals of the fast path
+    i64 mat_t = 0;        // entries of the thread-kernel groups
+    int n_groups = 0;
+};
 
 }  // namespace
 
@@ -338,8 +313,11 @@ void qb200_destroy(qb200_ctx_t *ctx)
     for (DevBuf *b : {&ctx->d_raw, &ctx->d_codes, &ctx->d_pairs, &ctx->d_peq, &ctx->d_peqjobs, &ctx->d_bound, &ctx->d_hew,
                       &ctx->d_score, &ctx->d_status, &ctx->d_textlen, &ctx->d_cigoff, &ctx->d_cigar, &ctx->d_counters,
                       &ctx->d_scan_tmp, &ctx->d_leaves, &ctx->d_leafout, &ctx->d_pairleaves, &ctx->d_work, &ctx->d_bandout,
-                      &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges})
+                      &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
+                      &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
+                      &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB})
         b->release();
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -408,30 +386,48 @@ int qb200_upload_device(qb200_ctx_t *ctx, const qb200_batch_t *b)
     return finish_upload(ctx);
 }
 
+// Host-driven slow path (WindowEd(L), band doubling, Hirschberg splits, WINDOWED, BANDED only_score): defined below.
+static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std::vector<int> &slow_pairs,
+                         i64 &n_leaves_total, i64 &ops_words_total, i64 &range_total, std::vector<PairLeaves> &slow_pl);
+
 int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
 {
     if (!ctx || !params) return QB200_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const quicked_params_t prm = *params;
     const i64 n = ctx->n_pairs;
-    // reset per-run stats (keep upload byte counts)
     const i64 h2d = ctx->stats.h2d_bytes;
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.h2d_bytes = h2d; ctx->stats.n_pairs = n; ctx->stats.cells = ctx->cells;
     ctx->ev_used = 0; ctx->ev_spans.clear();
-    ctx->h_score.assign((size_t)n, -1);
-    ctx->h_status.assign((size_t)n, QUICKED_ERROR);
-    ctx->have_cigar = false; ctx->cigar_total = 0;
+    ctx->have_cigar = false; ctx->cigar_total = 0; ctx->unknown_algo = false;
     if (n == 0) { ctx->ran = true; return 0; }
     if (prm.algo != QUICKED && prm.algo != BANDED && prm.algo != WINDOWED && prm.algo != HIRSCHBERG) {
-        std::fill(ctx->h_status.begin(), ctx->h_status.end(), (int)QUICKED_UNKNOWN_ALGO);   // quicked.c:433
+        ctx->unknown_algo = true;                                   // quicked.c:433: every pair -> QUICKED_UNKNOWN_ALGO
         ctx->ran = true;
         return 0;
     }
+    const int ni = (int)n;
+    const int nb256 = (ni + 255) / 256;
     cudaEvent_t ev_begin = new_event(ctx), ev_end = new_event(ctx);
     CK(cudaEventRecord(ev_begin, ctx->stream));
-    CK(ctx->d_counters.reserve(64));
-    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    CK(ctx->d_counters.reserve(256));
+    CK(cudaMemsetAsync(ctx->d_counters.p, 0, 256, ctx->stream));
+    CK(ctx->d_bound.reserve((size_t)n * 4));
+    CK(ctx->d_hew.reserve((size_t)n * 4));
+    CK(ctx->d_score.reserve((size_t)n * 4));
+    CK(ctx->d_status.reserve((size_t)n * 4));
+    CK(ctx->d_cls.reserve((size_t)n));
+    CK(ctx->d_cutoff.reserve((size_t)n * 8));
+    CK(ctx->d_plan_items.reserve((size_t)n * sizeof(PlanSum)));
+    CK(ctx->d_plan_offs.reserve((size_t)(n + 1) * sizeof(PlanSum)));
+    CK(ctx->d_pairleaves.reserve(sizeof(PairLeaves) * (size_t)n));
+    CK(ctx->d_textbytes.reserve((size_t)n * 8));
+    CK(ctx->d_cigoff.reserve((size_t)(n + 1) * 8));
+    CK(ctx->d_list_t.reserve((size_t)n * 4));
+    CK(ctx->d_list_w.reserve((size_t)n * 4));
+    CK(ctx->d_list_slow.reserve((size_t)n * 4));
+    if (!ctx->h_pinned) CK(cudaHostAlloc(&ctx->h_pinned, 4096, cudaHostAllocDefault));
 
     // ---- prepare: codes + forward match masks ----
     {
@@ -456,130 +452,208 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         }
     }
 
-    std::vector<i64> cutoff((size_t)n, 0);
-    std::vector<char> valid((size_t)n, 0);
-    for (i64 i = 0; i < n; ++i) {
-        const PairRec &r = ctx->h_pairs[(size_t)i];
-        valid[(size_t)i] = (r.m > 0 && r.n > 0);
-        if (!valid[(size_t)i]) ctx->h_status[(size_t)i] = QUICKED_EMPTY_SEQUENCE;          // quicked.c:411-414
-    }
-    const bool want_cigar = !prm.only_score;
-    int ok_status = QUICKED_WIP;
-
+    // ---- QUICKED stage 1: WindowEd(S) bound (quicked.c:178-199) ----
     if (prm.algo == QUICKED) {
-        // ---- stage 1: WindowEd(S) bound (quicked.c:178-199) ----
-        CK(ctx->d_bound.reserve((size_t)n * 4));
-        CK(ctx->d_hew.reserve((size_t)n * 4));
-        {
-            Span sp(ctx, ST_WS);
-            const int T = 64;
-            const size_t smem = (size_t)kWsSlots * T * 8;
-            const int blocks = (int)((n + T - 1) / T);
-            if (prm.force_scalar) {
-                CK(cudaFuncSetAttribute(k_windowed21_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_windowed21_score<false><<<blocks, T, smem, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), (int)n, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                    ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>());
-            } else {
-                CK(cudaFuncSetAttribute(k_windowed21_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_windowed21_score<true><<<blocks, T, smem, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), (int)n, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                    ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>());
-            }
-            CK(cudaGetLastError());
-            ctx->stats.kernel_launches++;
+        Span sp(ctx, ST_WS);
+        const int T = 64;
+        const size_t smem = (size_t)kWsSlots * T * 8;
+        const int blocks = (int)((n + T - 1) / T);
+        if (prm.force_scalar) {
+            CK(cudaFuncSetAttribute(k_windowed21_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_windowed21_score<false><<<blocks, T, smem, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>());
+        } else {
+            CK(cudaFuncSetAttribute(k_windowed21_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_windowed21_score<true><<<blocks, T, smem, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>());
         }
-        std::vector<int> h_bound((size_t)n), h_hew((size_t)n);
-        CK(cudaMemcpyAsync(h_bound.data(), ctx->d_bound.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(h_hew.data(), ctx->d_hew.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        for (i64 i = 0; i < n; ++i) {
-            if (!valid[(size_t)i]) continue;
-            const PairRec &r = ctx->h_pairs[(size_t)i];
-            const unsigned maxlen = (unsigned)std::max(r.m, r.n);
-            cutoff[(size_t)i] = h_bound[(size_t)i];
-            if ((i64)h_hew[(size_t)i] * 64 > (i64)(maxlen * prm.hew_percentage[0] / 100)) {   // quicked.c:201-202
-                ctx->stats.pairs_stage2++;
-                ctx->h_status[(size_t)i] = QUICKED_UNIMPLEMENTED;   // stages 2-3 arrive with the generic WindowEd kernel
-                valid[(size_t)i] = 0;
-            }
-        }
-    } else if (prm.algo == BANDED || prm.algo == HIRSCHBERG) {
-        for (i64 i = 0; i < n; ++i) {
-            const PairRec &r = ctx->h_pairs[(size_t)i];
-            cutoff[(size_t)i] = (i64)((unsigned)std::max(r.m, r.n) * prm.bandwidth / 100);        // quicked.c:64, :131
-        }
-        if (prm.algo == HIRSCHBERG) ok_status = QUICKED_OK;
-    } else {
-        for (i64 i = 0; i < n; ++i) if (valid[(size_t)i]) { ctx->h_status[(size_t)i] = QUICKED_UNIMPLEMENTED; valid[(size_t)i] = 0; }
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches++;
     }
 
-    // ---- alignment: leaves (no Hirschberg split yet) ----
-    std::vector<BandTask> leaves;
-    std::vector<PairLeaves> pl((size_t)n);
-    leaves.reserve((size_t)n);
-    for (i64 i = 0; i < n; ++i) {
-        pl[(size_t)i].first_leaf = (i64)leaves.size(); pl[(size_t)i].n_leaves = 0; pl[(size_t)i].pad_ = 0;
-        if (!valid[(size_t)i]) continue;
-        const PairRec &r = ctx->h_pairs[(size_t)i];
-        const BandGeom g = band_geometry(r.m, r.n, cutoff[(size_t)i]);
-        const bool split = (prm.algo != BANDED) && ((unsigned long long)g.Bc * (unsigned long long)r.n * 16ull > (1ull << 24));
-        if (split || (prm.algo == BANDED && prm.only_score)) {
-            ctx->h_status[(size_t)i] = QUICKED_UNIMPLEMENTED;
-            continue;
-        }
-        BandTask t{};
-        t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = 0; t.finish = r.n;
-        t.cutoff = cutoff[(size_t)i]; t.peq_off = r.peq_off; t.nbp = r.nbp; t.pair = (int)i;
-        leaves.push_back(t);
-        pl[(size_t)i].n_leaves = 1;
-        ctx->h_status[(size_t)i] = ok_status;
+    // ---- plan: classify every pair and lay out the pools with one scan ----
+    RunPlan plan;
+    {
+        Span sp(ctx, ST_PLAN);
+        PlanParams pp;
+        pp.algo = (int)prm.algo; pp.bandwidth = prm.bandwidth; pp.hew_pct0 = prm.hew_percentage[0];
+        pp.only_score = prm.only_score; pp.thread_band_max = kThreadBandMax;
+        pp.ok_status = (prm.algo == HIRSCHBERG) ? QUICKED_OK : QUICKED_WIP;
+        k_plan<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, pp, ctx->d_bound.as<int>(), ctx->d_hew.as<int>(),
+                                               ctx->d_plan_items.as<PlanSum>(), ctx->d_cls.as<unsigned char>(), ctx->d_cutoff.as<i64>(),
+                                               ctx->d_status.as<int>(), ctx->d_score.as<int>());
+        CK(cudaGetLastError());
+        size_t tmp = 0;
+        const PlanSum zero = {0, 0, 0, 0, 0, 0, 0, 0};
+        CK(cub::DeviceScan::ExclusiveScan(nullptr, tmp, ctx->d_plan_items.as<PlanSum>(), ctx->d_plan_offs.as<PlanSum>(), PlanAdd(), zero, ni, ctx->stream));
+        CK(ctx->d_scan_tmp.reserve(tmp + 256));
+        CK(cub::DeviceScan::ExclusiveScan(ctx->d_scan_tmp.p, tmp, ctx->d_plan_items.as<PlanSum>(), ctx->d_plan_offs.as<PlanSum>(), PlanAdd(), zero, ni, ctx->stream));
+        k_plan_totals<<<1, 32, 0, ctx->stream>>>(ctx->d_plan_items.as<PlanSum>(), ctx->d_plan_offs.as<PlanSum>(), ni, ctx->d_plan_offs.as<PlanSum>() + n);
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches += 4;
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_plan_offs.as<PlanSum>() + n, sizeof(PlanSum), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        plan.tot = *reinterpret_cast<PlanSum *>(ctx->h_pinned);
     }
-    int rc = run_leaves(ctx, leaves);
-    if (rc) return rc;
+    const PlanSum &tot = plan.tot;
+
+    // ---- slow path first (it appends its leaves after the fast ones and returns its pool usage) ----
+    i64 n_leaves = tot.leaf, ops_words = tot.ops, range_ints = tot.rng;
+    std::vector<PairLeaves> slow_pl;
+    std::vector<int> slow_pairs;
+    if (tot.slow > 0) {
+        slow_pairs.resize((size_t)tot.slow);
+    }
+    CK(ctx->d_leaves.reserve(sizeof(BandTask) * (size_t)std::max<i64>(n_leaves, 1)));
+    if (tot.leaf > 0 || tot.slow > 0) {
+        k_build_leaves<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_cls.as<unsigned char>(), ctx->d_cutoff.as<i64>(),
+                                                       ctx->d_plan_offs.as<PlanSum>(), ctx->d_leaves.as<BandTask>(), ctx->d_list_t.as<int>(),
+                                                       ctx->d_list_w.as<int>(), ctx->d_list_slow.as<int>(), ctx->d_pairleaves.as<PairLeaves>());
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    if (tot.slow > 0) {
+        CK(cudaMemcpyAsync(slow_pairs.data(), ctx->d_list_slow.p, (size_t)tot.slow * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    // thread-kernel groups
+    if (tot.t > 0) {
+        plan.n_groups = (int)((tot.t + 31) / 32);
+        CK(ctx->d_gsize.reserve((size_t)plan.n_groups * 8));
+        CK(ctx->d_goff.reserve((size_t)(plan.n_groups + 1) * 8));
+        CK(ctx->d_gB.reserve((size_t)plan.n_groups * 4));
+        k_group_size<<<(plan.n_groups * 32 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_list_t.as<int>(), (int)tot.t, ctx->d_leaves.as<BandTask>(),
+                                                                                  ctx->d_gsize.as<i64>(), ctx->d_gB.as<int>());
+        CK(cudaGetLastError());
+        size_t tmp = 0;
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_gsize.as<i64>(), ctx->d_goff.as<i64>(), plan.n_groups, ctx->stream));
+        CK(ctx->d_scan_tmp.reserve(tmp + 256));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp.p, tmp, ctx->d_gsize.as<i64>(), ctx->d_goff.as<i64>(), plan.n_groups, ctx->stream));
+        k_last_offset<<<1, 32, 0, ctx->stream>>>(ctx->d_goff.as<i64>(), ctx->d_gsize.as<i64>(), plan.n_groups, reinterpret_cast<i64 *>(ctx->d_counters.as<u64>() + 16),
+                                                 ctx->d_goff.as<i64>() + plan.n_groups);
+        k_group_assign<<<(int)((tot.t + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_list_t.as<int>(), (int)tot.t, ctx->d_leaves.as<BandTask>(),
+                                                                             ctx->d_goff.as<i64>(), ctx->d_gB.as<int>(), tot.matw);
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches += 5;
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.as<u64>() + 16, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        plan.mat_t = *reinterpret_cast<i64 *>(ctx->h_pinned);
+    }
+
+    // pools of the fast path
+    CK(ctx->d_ops.reserve((size_t)std::max<i64>(ops_words, 1) * 4 + 16));
+    CK(ctx->d_ranges.reserve((size_t)std::max<i64>(range_ints, 1) * 8 + 16));
+    CK(ctx->d_leafout.reserve(sizeof(LeafOut) * (size_t)std::max<i64>(n_leaves, 1)));
+    CK(ctx->d_bandout.reserve(sizeof(BandOut) * (size_t)std::max<i64>(n_leaves, 1)));
+    if (tot.sc > 0) {
+        CK(ctx->d_scores.reserve((size_t)tot.sc * 4 + 16));
+        CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)tot.sc * 4, ctx->stream));
+    }
+
+    // ---- fast path: fill + traceback, chunked only if the traceback state exceeds the pool ----
+    if (tot.leaf > 0) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, (size_t)((free_b + ctx->d_matrix.cap) * 0.85)) / 16);
+        const i64 need = tot.matw + plan.mat_t;
+        if (need <= limit) {
+            CK(ctx->d_matrix.reserve((size_t)need * 16));
+            {
+                Span sp(ctx, ST_FILL);
+                int rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), 0, (int)tot.t, 0);
+                if (!rc) rc = launch_banded<true>(ctx, 63u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0);
+                if (rc) return rc;
+            }
+            {
+                Span sp(ctx, ST_TRACE);
+                int rc = launch_traceback(ctx, nullptr, 0, (int)tot.leaf, 0);
+                if (rc) return rc;
+            }
+            ctx->stats.matrix_bytes += need * 16;
+        } else {
+            CK(ctx->d_matrix.reserve((size_t)limit * 16));
+            int *d_idx = reinterpret_cast<int *>(ctx->d_counters.as<u64>() + 20);
+            i64 *d_off = reinterpret_cast<i64 *>(ctx->d_counters.as<u64>() + 22);
+            // warp-kernel leaves
+            for (int s0 = 0; s0 < (int)tot.w;) {
+                k_chunk_end_leaves<<<1, 1, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), (int)tot.w, s0, limit, d_idx, d_off);
+                CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 24, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                const int s1 = *reinterpret_cast<int *>(ctx->h_pinned);
+                const i64 sub = *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
+                { Span sp(ctx, ST_FILL); int rc = launch_banded<true>(ctx, 63u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
+                { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
+                s0 = s1;
+            }
+            // thread-kernel groups
+            for (int g0 = 0; g0 < plan.n_groups;) {
+                k_chunk_end_groups<<<1, 1, 0, ctx->stream>>>(ctx->d_goff.as<i64>(), ctx->d_gsize.as<i64>(), plan.n_groups, g0, limit, d_idx);
+                CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->h_pinned + 16, ctx->d_goff.as<i64>() + g0, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                const int g1 = *reinterpret_cast<int *>(ctx->h_pinned);
+                const i64 sub = tot.matw + *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
+                const int q0 = g0 * 32, q1 = (int)std::min<i64>(tot.t, (i64)g1 * 32);
+                { Span sp(ctx, ST_FILL); int rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), q0, q1 - q0, sub); if (rc) return rc; }
+                { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_list_t.as<int>(), q0, q1 - q0, sub); if (rc) return rc; }
+                g0 = g1;
+            }
+            ctx->stats.matrix_bytes += need * 16;
+        }
+        ctx->stats.leaves += tot.leaf;
+    }
+
+    // ---- slow path ----
+    if (tot.slow > 0) {
+        int rc = run_slow_path(ctx, prm, slow_pairs, n_leaves, ops_words, range_ints, slow_pl);
+        if (rc) return rc;
+    }
 
     // ---- scores + CIGAR text ----
-    if (!leaves.empty()) {
-        std::vector<LeafOut> lo(leaves.size());
-        rc = emit_results(ctx, pl, want_cigar);
-        if (rc) return rc;
-        CK(cudaMemcpyAsync(lo.data(), ctx->d_leafout.p, sizeof(LeafOut) * lo.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        for (i64 i = 0; i < n; ++i) {
-            const PairLeaves &p = pl[(size_t)i];
-            if (!p.n_leaves) continue;
-            int s = 0;
-            for (int l = 0; l < p.n_leaves; ++l) s += lo[(size_t)p.first_leaf + l].cost;
-            ctx->h_score[(size_t)i] = s;                                   // cigar_score_edit, quicked.c:54
-        }
-    }
-    if (want_cigar) {
-        // offsets: exclusive scan of (text_len + 1); pairs without leaves get an empty string
+    const bool want_cigar = !prm.only_score;
+    {
         Span sp(ctx, ST_CIGAR);
-        std::vector<int> tl((size_t)n + 1, 0);
-        if (!leaves.empty()) CK(cudaMemcpyAsync(tl.data(), ctx->d_textlen.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        std::vector<i64> off((size_t)n + 1);
-        i64 acc = 0;
-        for (i64 i = 0; i < n; ++i) { off[(size_t)i] = acc; acc += (pl[(size_t)i].n_leaves ? tl[(size_t)i] : 0) + 1; }
-        off[(size_t)n] = acc;
-        ctx->cigar_total = acc;
-        CK(ctx->d_cigar.reserve((size_t)acc + 16));
-        CK(cudaMemsetAsync(ctx->d_cigar.p, 0, (size_t)acc, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_cigoff.p, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        if (!leaves.empty()) {
-            k_cigar_text<true><<<(int)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), (int)n, ctx->d_leaves.as<BandTask>(),
-                ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), nullptr, ctx->d_cigoff.as<i64>(), ctx->d_cigar.as<char>());
+        k_pair_finish<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leafout.as<LeafOut>(), ctx->d_status.as<int>(),
+                                                      ctx->d_score.as<int>(), ctx->d_textbytes.as<i64>(), want_cigar ? 1 : 0);
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        if (want_cigar) {
+            if (ctx->multi_leaf_pairs) {
+                CK(ctx->d_textlen.reserve((size_t)n * 4));
+                k_cigar_text<false><<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leaves.as<BandTask>(),
+                    ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), ctx->d_textlen.as<int>(), nullptr, nullptr);
+                k_merge_text_len<<<nb256, 256, 0, ctx->stream>>>(ctx->d_textlen.as<int>(), ctx->d_textbytes.as<i64>(), ni);
+                CK(cudaGetLastError());
+                ctx->stats.kernel_launches += 2;
+            }
+            size_t tmp = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_textbytes.as<i64>(), ctx->d_cigoff.as<i64>(), ni, ctx->stream));
+            CK(ctx->d_scan_tmp.reserve(tmp + 256));
+            CK(cub::DeviceScan::ExclusiveSum(ctx->d_scan_tmp.p, tmp, ctx->d_textbytes.as<i64>(), ctx->d_cigoff.as<i64>(), ni, ctx->stream));
+            k_last_offset<<<1, 32, 0, ctx->stream>>>(ctx->d_cigoff.as<i64>(), ctx->d_textbytes.as<i64>(), ni, reinterpret_cast<i64 *>(ctx->d_counters.as<u64>() + 24),
+                                                     ctx->d_cigoff.as<i64>() + n);
             CK(cudaGetLastError());
-            ctx->stats.kernel_launches++;
+            ctx->stats.kernel_launches += 3;
+            CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_counters.as<u64>() + 24, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->cigar_total = *reinterpret_cast<i64 *>(ctx->h_pinned);
+            CK(ctx->d_cigar.reserve((size_t)ctx->cigar_total + 16));
+            CK(cudaMemsetAsync(ctx->d_cigar.p, 0, (size_t)ctx->cigar_total, ctx->stream));
+            if (n_leaves > 0) {
+                k_cigar_text<true><<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leaves.as<BandTask>(),
+                    ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), nullptr, ctx->d_cigoff.as<i64>(), ctx->d_cigar.as<char>());
+                CK(cudaGetLastError());
+                ctx->stats.kernel_launches++;
+            }
+            ctx->have_cigar = true;
         }
-        ctx->have_cigar = true;
-        ctx->h_cigoff_.swap(off);   // host copy of the offsets for qb200_download
     }
     CK(cudaEventRecord(ev_end, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
 
     // ---- stats ----
-    u64 counters[8];
-    CK(cudaMemcpy(counters, ctx->d_counters.p, 64, cudaMemcpyDeviceToHost));
+    u64 counters[4];
+    CK(cudaMemcpy(counters, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost));
     ctx->stats.word_steps_windowed = (i64)counters[0];
     ctx->stats.word_steps_banded = (i64)counters[1];
     ctx->stats.word_steps = (i64)(counters[0] + counters[1]);
@@ -587,11 +661,24 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     cudaEventElapsedTime(&ms, ev_begin, ev_end);
     ctx->stats.ms_total = ms;
     float st[ST_COUNT] = {0};
-    for (auto &s : ctx->ev_spans) { float t = 0; cudaEventElapsedTime(&t, s.second.first, s.second.second); st[s.first] += t; }
-    ctx->stats.ms_prepare = st[ST_PREP]; ctx->stats.ms_windowed_s = st[ST_WS]; ctx->stats.ms_windowed_l = st[ST_WL];
+    for (auto &sp : ctx->ev_spans) { float t = 0; cudaEventElapsedTime(&t, sp.second.first, sp.second.second); st[sp.first] += t; }
+    ctx->stats.ms_prepare = st[ST_PREP] + st[ST_PLAN]; ctx->stats.ms_windowed_s = st[ST_WS]; ctx->stats.ms_windowed_l = st[ST_WL];
     ctx->stats.ms_banded = st[ST_BANDED]; ctx->stats.ms_align_fill = st[ST_FILL]; ctx->stats.ms_align_trace = st[ST_TRACE];
     ctx->stats.ms_cigar = st[ST_CIGAR];
     ctx->ran = true;
+    return 0;
+}
+
+static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std::vector<int> &slow_pairs,
+                         i64 &n_leaves_total, i64 &ops_words_total, i64 &range_total, std::vector<PairLeaves> &slow_pl)
+{
+    // Not implemented yet: the pairs keep QUICKED_UNIMPLEMENTED so the caller sees a loud, per-pair error.
+    (void)prm; (void)n_leaves_total; (void)ops_words_total; (void)range_total; (void)slow_pl;
+    std::vector<int> st(slow_pairs.size(), (int)QUICKED_UNIMPLEMENTED);
+    for (size_t q = 0; q < slow_pairs.size(); ++q)
+        CK(cudaMemcpyAsync(ctx->d_status.as<int>() + slow_pairs[q], &st[q], 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.pairs_stage2 += (i64)slow_pairs.size();
     return 0;
 }
 
@@ -600,27 +687,63 @@ int qb200_download(qb200_ctx_t *ctx, qb200_results_t *res)
     if (!ctx || !res || !ctx->ran) return QB200_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const i64 n = ctx->n_pairs;
-    if (res->score) memcpy(res->score, ctx->h_score.data(), (size_t)n * 4);
-    if (res->status) memcpy(res->status, ctx->h_status.data(), (size_t)n * 4);
-    ctx->stats.d2h_bytes += n * 8;
     res->cigar_bytes = 0;
+    if (ctx->unknown_algo) {
+        for (i64 i = 0; i < n; ++i) { if (res->score) res->score[i] = -1; if (res->status) res->status[i] = QUICKED_UNKNOWN_ALGO; }
+        if (res->cigar_off) for (i64 i = 0; i <= n; ++i) res->cigar_off[i] = 0;
+        return 0;
+    }
+    if (n == 0) { if (res->cigar_off) res->cigar_off[0] = 0; return 0; }
+    if (res->score) CK(cudaMemcpyAsync(res->score, ctx->d_score.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (res->status) CK(cudaMemcpyAsync(res->status, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n * 8;
+    int rc = 0;
     if (ctx->have_cigar && res->cigar_off) {
-        memcpy(res->cigar_off, ctx->h_cigoff_.data(), (size_t)(n + 1) * 8);
+        CK(cudaMemcpyAsync(res->cigar_off, ctx->d_cigoff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (n + 1) * 8;
         res->cigar_bytes = ctx->cigar_total;
-        if (!res->cigar || res->cigar_capacity < ctx->cigar_total) return QB200_ERR_CAPACITY;
-        CK(cudaMemcpyAsync(res->cigar, ctx->d_cigar.p, (size_t)ctx->cigar_total, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        ctx->stats.d2h_bytes += ctx->cigar_total;
+        if (!res->cigar || res->cigar_capacity < ctx->cigar_total) rc = QB200_ERR_CAPACITY;
+        else {
+            CK(cudaMemcpyAsync(res->cigar, ctx->d_cigar.p, (size_t)ctx->cigar_total, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->stats.d2h_bytes += ctx->cigar_total;
+        }
     } else if (res->cigar_off) {
         for (i64 i = 0; i <= n; ++i) res->cigar_off[i] = 0;
     }
-    return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
 }
 
 int qb200_get_stats(qb200_ctx_t *ctx, qb200_stats_t *stats)
 {
     if (!ctx || !stats) return QB200_ERR_ARG;
     *stats = ctx->stats;
+    return 0;
+}
+
+int qb200_measure_int_peak(qb200_ctx_t *ctx, double *tera_ops_per_s)
+{
+    if (!ctx || !tera_ops_per_s) return QB200_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_counters.reserve(64));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int blocks = sms * 8, iters = 4096;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(a, ctx->stream));
+        k_int_peak<<<blocks, 256, 0, ctx->stream>>>(ctx->d_counters.as<u32>() + 8, iters, 0x5bd1e995u + rep, 0x9e3779b9u, 0x85ebca6bu);
+        CK(cudaEventRecord(b, ctx->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        const double ops = (double)blocks * 256.0 * iters * 8.0 * 8.0 * 2.0;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tera_ops_per_s = best;
     return 0;
 }
 

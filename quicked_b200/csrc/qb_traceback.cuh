@@ -55,13 +55,14 @@ __device__ __forceinline__ bool cell_written(const int2 *ranges, int B, int c, i
 
 // One leaf per thread: simple pointer-chasing walk over the [column][band word] matrix written by k_banded_warp<.,true>.
 __global__ void __launch_bounds__(128)
-k_traceback_thread(const BandTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ raw,
-                   const ulonglong2 *__restrict__ matrix, const int2 *__restrict__ range_pool,
-                   u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
+k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
+                   const unsigned char *__restrict__ raw, const ulonglong2 *__restrict__ matrix,
+                   const int2 *__restrict__ range_pool, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
 {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= n_tasks) return;
-    const BandTask tk = tasks[id];
+    BandTask tk = tasks[list ? list[begin + id] : begin + id];
+    tk.mat_off -= mat_sub;
     const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
     const int B = (int)g.Bc, prolog = (int)g.prolog;
     const ulonglong2 *mat = matrix + tk.mat_off;
@@ -74,8 +75,8 @@ k_traceback_thread(const BandTask *__restrict__ tasks, int n_tasks, const unsign
         const int evr = v - 64 * (((h + 1) >> 6) - prolog);
         const int wr = evr >> 6, wl = ev >> 6;
         u64 pvw = 0, mvw = 0;
-        if (cell_written(ranges, B, h + 1, wr)) pvw = mat[(i64)(h + 1) * B + wr].x;
-        if (cell_written(ranges, B, h, wl)) mvw = mat[(i64)h * B + wl].y;
+        if (cell_written(ranges, B, h + 1, wr)) pvw = mat[(i64)(h + 1) * tk.mat_cs + (i64)wr * tk.mat_ws].x;
+        if (cell_written(ranges, B, h, wl)) mvw = mat[(i64)h * tk.mat_cs + (i64)wl * tk.mat_ws].y;
         if ((pvw >> (evr & 63)) & 1ull) { w.emit(OP_D); --v; }
         else if ((mvw >> (ev & 63)) & 1ull) { w.emit(OP_I); --h; }
         else { w.emit(traw[h] == praw[v] ? OP_M : OP_X); --h; --v; }
@@ -116,6 +117,8 @@ k_cigar_text(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask *__r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const PairLeaves p = pl[i];
+    if (!WRITE && p.n_leaves < 2) return;        // single-leaf lengths come from the traceback itself
+    if (WRITE && p.n_leaves == 0) return;        // empty string: the buffer is pre-zeroed
     char *dst = WRITE ? cigar + cigar_off[i] : nullptr;
     int out = 0, cur_op = -1, cur_len = 0;
     for (int l = 0; l < p.n_leaves; ++l) {

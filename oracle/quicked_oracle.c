@@ -243,9 +243,14 @@ static int64_t banded_full(const pat_t *p, const char *text, int64_t n, int64_t 
     while (v >= 0 && h >= 0) {
         const int64_t ev = v - W64 * (h / W64 - prolog);
         const int64_t ev_r = v - W64 * ((h + 1) / W64 - prolog);
-        const uint64_t pvw = PV[(h + 1) * B + ev_r / W64], mvw = MV[h * B + ev / W64];
-        if (pvw & (1ull << (ev_r % W64))) { ops_push_front(out, 'D'); --v; }
-        else if (mvw & (1ull << (ev % W64))) { ops_push_front(out, 'I'); --h; }
+        /* A too-narrow band can put v outside the band's coordinates: the reference then indexes the flat
+         * [column][word] array with a C-truncated (possibly negative) word number and shifts by a count the CPU
+         * masks to 6 bits (bpm_banded.c:995-1000).  Reproduce exactly that; outside the allocation read 0. */
+        const int64_t fr = (h + 1) * B + ev_r / W64, fl = h * B + ev / W64;
+        const int64_t cells = B * (n + 1);
+        const uint64_t pvw = (fr >= 0 && fr < cells) ? PV[fr] : 0, mvw = (fl >= 0 && fl < cells) ? MV[fl] : 0;
+        if (pvw & (1ull << (ev_r & 63))) { ops_push_front(out, 'D'); --v; }
+        else if (mvw & (1ull << (ev & 63))) { ops_push_front(out, 'I'); --h; }
         else { ops_push_front(out, text[h] == p->raw[v] ? 'M' : 'X'); --h; --v; }
     }
     while (h >= 0) { ops_push_front(out, 'I'); --h; }

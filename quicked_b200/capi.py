@@ -261,7 +261,7 @@ class BatchAligner:
         return s.as_dict()
 
     def align(self, pairs, params=None, **kw):
-        """-> list of (status, score, cigar-or-None), same tuple shape as the oracle harness"""
+        """-> list of (status, score, cigar-or-None), one tuple per pair"""
         self.upload_arrays(*pack_pairs(pairs))
         self.run(params, **kw)
         status, score, off, cig = self.download()

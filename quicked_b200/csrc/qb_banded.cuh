@@ -54,7 +54,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
     const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
     const int B = (int)(FULL ? g.Bc : g.Bs);
     {   // tasks of other band heights are handled by the launch of their own R (one list, one launch per R)
-        const int need = B <= 32 ? 1 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : 32;
+        const int need = B <= 32 ? 1 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : B <= 1024 ? 32 : 64;
         if (need != R) return;
     }
     const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63;
@@ -202,6 +202,136 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
     if (lane == 0) {
         BandOut o;
         const int sfin = scores[nblk - 1];                            // bpm_banded.c:952-961
+        o.score = mmod ? sfin - (64 - mmod) : sfin;
+        o.first = first; o.last = last; o.pos_v = pos_v;
+        outs[tk.slot] = o;
+        atomicAdd(&counters[1], ws);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_banded_warp_dyn<FULL>: the same algorithm for bands taller than 1024 blocks (e.g. the stage-3 pass of a 500 kbp
+// ONT pair at 15 % bandwidth: 1194 blocks).  One warp per CTA; Pv / Mv / scores of the whole band stay in shared
+// memory (20 bytes per block, up to ~11 000 blocks) and the warp sweeps the band in rounds of 32 blocks per column.
+// Correctness path for rare, very long pairs: throughput comes from the R-templated kernel above.
+template <bool FULL>
+__global__ void __launch_bounds__(32)
+k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
+                  const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
+                  int *__restrict__ scores_pool, u64 *__restrict__ state_pool, int2 *__restrict__ range_pool,
+                  BandOut *__restrict__ outs, u64 *__restrict__ counters, int cap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int task_id = blockIdx.x;
+    if (task_id >= n_tasks) return;
+    BandTask tk = tasks[list ? list[begin + task_id] : begin + task_id];
+    tk.mat_off -= mat_sub;
+    const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+    const int B = (int)(FULL ? g.Bc : g.Bs);
+    if (B <= 1024) return;                                           // handled by the R-templated launches
+    u64 *s_pv = reinterpret_cast<u64 *>(smem_raw);
+    u64 *s_mv = s_pv + cap;
+    const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63;
+    const int clamp = FULL ? nblk - 1 : nblk;
+    const int prolog = (int)g.prolog;
+    const i64 fin = g.fin, kcut = g.k;
+    const u64 *pq = peq + tk.peq_off;
+    int *scores = scores_pool + tk.scores_off;
+    const unsigned char *tcodes = codes + tk.t_off;
+    const int ncols = FULL ? tk.n : tk.finish;
+    int first = prolog, last = B - 1, pos_v = -prolog, pos_h = 0;
+    int2 *ranges = FULL ? range_pool + tk.range_off : nullptr;
+    if (FULL && lane == 0) ranges[0] = make_int2(first, last);
+    for (int j = lane; j < B; j += 32) {
+        scores[j] = 64 * (j + 1);
+        const int blk = j + pos_v;
+        if (blk >= 0) { s_pv[blk % cap] = ~0ull; s_mv[blk % cap] = 0ull; }
+        if (FULL) matrix[tk.mat_off + j] = make_ulonglong2(~0ull, 0ull);
+    }
+    __syncwarp();
+    u64 ws = 0;
+    for (int col = 0; col < ncols; ++col) {
+        unsigned char code = tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col];
+        u32 cin = 0, hp_carry = 1;
+        const bool store_col = FULL && ((col & 63) != 63);
+        for (int j0 = first; j0 <= last; j0 += 32) {
+            const int j = j0 + lane;
+            const bool act = j <= last;
+            const int blk = j + pos_v, slot = act ? blk % cap : 0;
+            const u64 eq = (act && blk < tk.nbp) ? pq[(i64)code * tk.nbp + blk] : 0ull;
+            u64 pv = act ? s_pv[slot] : 0ull, mv = act ? s_mv[slot] : 0ull;
+            const int ob = (blk == nblk - 1 && mmod) ? mmod - 1 : 63;
+            const u64 a = eq & pv, s = a + pv;
+            const u32 G = __ballot_sync(kFull, act && (s < a));
+            const u32 P = __ballot_sync(kFull, act && (s == ~0ull));
+            const u32 X = G | P;
+            const u64 sum = (u64)X + (u64)G + (u64)cin;
+            const u32 carries = (u32)sum ^ X ^ G;
+            const u32 my_c = (carries >> lane) & 1u;
+            const u64 xh = ((s + my_c) ^ pv) | eq;
+            u64 ph = mv | ~(xh | pv);
+            u64 mh = pv & xh;
+            const u32 HP = __ballot_sync(kFull, (ph >> 63) != 0);
+            const u32 hp_in = lane ? ((HP >> (lane - 1)) & 1u) : hp_carry;
+            const int dsc = (int)((ph >> ob) & 1ull) - (int)((mh >> ob) & 1ull);
+            ph = (ph << 1) | (u64)hp_in;
+            mh = (mh << 1) | (u64)my_c;
+            const u64 xv = eq | mv;
+            pv = mh | ~(xv | ph);
+            mv = ph & xv;
+            if (act) {
+                s_pv[slot] = pv; s_mv[slot] = mv; scores[blk] += dsc;
+                if (store_col) matrix[tk.mat_off + (i64)(col + 1) * B + j] = make_ulonglong2(pv, mv);
+            }
+            cin = (u32)(sum >> 32);
+            hp_carry = HP >> 31;
+        }
+        ws += (u64)max(last - first + 1, 0);
+        __syncwarp();
+        if ((col & 63) != 63) continue;
+        {   // end of a 64-column block
+            const int col0 = col - 63;
+            const bool cut_lo = (first + 2 < last) && (fin > 64 * (i64)(first + 1)) &&
+                                ((i64)scores[first + pos_v + 1] + (fin - 64 * (i64)(first + 1)) > kcut);
+            const int first_old = first;
+            if (cut_lo && pos_h >= prolog) ++first;
+            else if (!cut_lo && pos_h < prolog) --first;
+            const int nb = last + pos_v + 1;
+            __syncwarp();
+            if (lane == 0) { s_pv[nb % cap] = ~0ull; s_mv[nb % cap] = 0ull; scores[nb] = scores[nb - 1] + 64; }
+            __syncwarp();
+            if (FULL) {
+                if (first > first_old && lane == 0) {
+                    const int blk = first_old + pos_v;
+                    matrix[tk.mat_off + (i64)(col0 + 64) * B + first_old] = make_ulonglong2(s_pv[blk % cap], s_mv[blk % cap]);
+                }
+                for (int j = first + lane; j <= last; j += 32) {
+                    const int blk = j + pos_v + 1;
+                    matrix[tk.mat_off + (i64)(col0 + 64) * B + j] = make_ulonglong2(s_pv[blk % cap], s_mv[blk % cap]);
+                }
+            }
+            const bool cut_hi = (first + 2 < last) && (64 * (i64)(last - 1) > fin) &&
+                                ((i64)scores[last + pos_v - 1] + (64 * (i64)(last - 1) - fin) > kcut);
+            if (cut_hi || (pos_v + last >= clamp)) --last;
+            ++pos_v; ++pos_h;
+            if (FULL && lane == 0) ranges[pos_h] = make_int2(first, last);
+        }
+        __syncwarp();
+    }
+    if (!FULL) {
+        u64 *st = state_pool + tk.state_off;
+        for (int j = lane; j < B; j += 32) {
+            const int blk = j + pos_v;
+            const bool act = (j >= first && j <= last && blk >= 0);
+            st[j] = act ? s_pv[blk % cap] : 0ull;
+            st[B + j] = act ? s_mv[blk % cap] : 0ull;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        BandOut o;
+        const int sfin = scores[nblk - 1];
         o.score = mmod ? sfin - (64 - mmod) : sfin;
         o.first = first; o.last = last; o.pos_v = pos_v;
         outs[tk.slot] = o;

@@ -18,6 +18,7 @@
 
 #include "qb_banded.cuh"
 #include "qb_common.cuh"
+#include "qb_hirschberg.cuh"
 #include "qb_plan.cuh"
 #include "qb_prep.cuh"
 #include "qb_traceback.cuh"
@@ -49,6 +50,18 @@ struct DevBuf {
         cap = want;
         return e;
     }
+    cudaError_t grow_keep(size_t bytes, size_t keep, cudaStream_t st)   // like reserve() but the first `keep` bytes survive
+    {
+        if (bytes <= cap) return cudaSuccess;
+        void *q = nullptr;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) return e;
+        if (p && keep) { e = cudaMemcpyAsync(q, p, keep, cudaMemcpyDeviceToDevice, st); if (e == cudaSuccess) e = cudaStreamSynchronize(st); }
+        if (p) cudaFree(p);
+        p = q; cap = want;
+        return e;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
@@ -76,6 +89,7 @@ struct qb200_ctx {
     DevBuf d_leaves, d_leafout, d_pairleaves, d_work, d_bandout, d_matrix, d_scores, d_state, d_ops, d_ranges;
     DevBuf d_cls, d_cutoff, d_plan_items, d_plan_offs, d_textbytes, d_list_t, d_list_w, d_list_slow, d_gsize, d_goff, d_gB;
     unsigned char *h_pinned = nullptr;     // small pinned mailbox for totals
+    DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
     std::vector<int> h_score, h_status;
     std::vector<i64> h_cigoff_;
@@ -185,7 +199,7 @@ int finish_upload(qb200_ctx *ctx)
 }
 
 template <int R, bool FULL>
-int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub)
+int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base)
 {
     if (n_tasks <= 0) return 0;
     const int bpw = BandedSmem<R>::kBytesPerWarp;
@@ -195,7 +209,7 @@ int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, 
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (n_tasks + wpb - 1) / wpb;
     kern<<<blocks, wpb * 32, smem, ctx->stream>>>(d_tasks, d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(),
-                                                   ctx->d_peq.as<u64>(), ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(),
+                                                   peq_base, ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(),
                                                    ctx->d_state.as<u64>(), ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(),
                                                    ctx->d_counters.as<u64>());
     CK(cudaGetLastError());
@@ -203,35 +217,56 @@ int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, 
     return 0;
 }
 
-int rounds_for(i64 B)
+constexpr i64 kDynBandMax = 11000;     // blocks whose Pv/Mv (16 B each) fit one CTA's shared memory
+int rounds_for(i64 B)                  // 64 = the dynamic (shared-memory resident) kernel
 {
     for (int r : {1, 2, 4, 8, 16, 32}) if (B <= 32 * r) return r;
+    return B <= kDynBandMax ? 64 : 0;
+}
+
+template <bool FULL>
+int launch_banded_dyn(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base)
+{
+    if (n_tasks <= 0) return 0;
+    const int cap = (int)kDynBandMax + 2;
+    const size_t smem = (size_t)cap * 16;
+    auto kern = k_banded_warp_dyn<FULL>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_tasks, 32, smem, ctx->stream>>>(d_tasks, d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(), peq_base,
+                                             ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(), ctx->d_state.as<u64>(),
+                                             ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(), ctx->d_counters.as<u64>(), cap);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
     return 0;
 }
 
 // One launch per band-height class present in the list (each warp exits at once if its task belongs to another class).
 template <bool FULL>
-int launch_banded(qb200_ctx *ctx, unsigned r_mask, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub)
+int launch_banded(qb200_ctx *ctx, unsigned r_mask, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub,
+                  const u64 *peq_base = nullptr)
 {
+    if (!peq_base) peq_base = ctx->d_peq.as<u64>();
     int rc = 0;
-    if (!rc && (r_mask & 1)) rc = launch_banded_r<1, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
-    if (!rc && (r_mask & 2)) rc = launch_banded_r<2, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
-    if (!rc && (r_mask & 4)) rc = launch_banded_r<4, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
-    if (!rc && (r_mask & 8)) rc = launch_banded_r<8, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
-    if (!rc && (r_mask & 16)) rc = launch_banded_r<16, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
-    if (!rc && (r_mask & 32)) rc = launch_banded_r<32, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub);
+    if (!rc && (r_mask & 1)) rc = launch_banded_r<1, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
+    if (!rc && (r_mask & 2)) rc = launch_banded_r<2, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
+    if (!rc && (r_mask & 4)) rc = launch_banded_r<4, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
+    if (!rc && (r_mask & 8)) rc = launch_banded_r<8, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
+    if (!rc && (r_mask & 16)) rc = launch_banded_r<16, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
+    if (!rc && (r_mask & 32)) rc = launch_banded_r<32, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
+    if (!rc && (r_mask & 64)) rc = launch_banded_dyn<FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
     return rc;
 }
 
 constexpr int kThreadBandMax = 4;
 
-int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub)
+int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base = nullptr)
 {
     if (n_tasks <= 0) return 0;
+    if (!peq_base) peq_base = ctx->d_peq.as<u64>();
     const int T = 128;
     const size_t smem = (size_t)kThreadBandMax * kAlpha * T * 8;
     k_banded_thread<kThreadBandMax><<<(n_tasks + T - 1) / T, T, smem, ctx->stream>>>(
-        ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
+        ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(), peq_base,
         ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(), ctx->d_counters.as<u64>());
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
@@ -315,7 +350,8 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_scan_tmp, &ctx->d_leaves, &ctx->d_leafout, &ctx->d_pairleaves, &ctx->d_work, &ctx->d_bandout,
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
                       &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
-                      &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB})
+                      &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB, &ctx->d_peq2, &ctx->d_jobs2, &ctx->d_tasks2, &ctx->d_wintasks,
+                      &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -400,7 +436,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.h2d_bytes = h2d; ctx->stats.n_pairs = n; ctx->stats.cells = ctx->cells;
     ctx->ev_used = 0; ctx->ev_spans.clear();
-    ctx->have_cigar = false; ctx->cigar_total = 0; ctx->unknown_algo = false;
+    ctx->have_cigar = false; ctx->cigar_total = 0; ctx->unknown_algo = false; ctx->multi_leaf_pairs = false;
     if (n == 0) { ctx->ran = true; return 0; }
     if (prm.algo != QUICKED && prm.algo != BANDED && prm.algo != WINDOWED && prm.algo != HIRSCHBERG) {
         ctx->unknown_algo = true;                                   // quicked.c:433: every pair -> QUICKED_UNKNOWN_ALGO
@@ -561,7 +597,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
             {
                 Span sp(ctx, ST_FILL);
                 int rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), 0, (int)tot.t, 0);
-                if (!rc) rc = launch_banded<true>(ctx, 63u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0);
+                if (!rc) rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0);
                 if (rc) return rc;
             }
             {
@@ -581,7 +617,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
                 CK(cudaStreamSynchronize(ctx->stream));
                 const int s1 = *reinterpret_cast<int *>(ctx->h_pinned);
                 const i64 sub = *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
-                { Span sp(ctx, ST_FILL); int rc = launch_banded<true>(ctx, 63u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
+                { Span sp(ctx, ST_FILL); int rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
                 { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
                 s0 = s1;
             }
@@ -669,16 +705,471 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     return 0;
 }
 
+namespace {
+
+struct HNode { int pair; i64 p_off, t_off; int m, n; i64 cutoff; };
+
+// Build match-mask tables for `jobs` in the slow-path pool (d_peq2); fills job.peq_off.
+int build_tables(qb200_ctx *ctx, std::vector<PeqJob> &jobs)
+{
+    if (jobs.empty()) return 0;
+    i64 words = 0;
+    for (auto &j : jobs) { j.peq_off = words; words += (i64)kAlpha * ((j.m + 63) / 64 + 2); }
+    CK(ctx->d_peq2.reserve((size_t)words * 8 + 64));
+    CK(ctx->d_jobs2.reserve(sizeof(PeqJob) * jobs.size()));
+    CK(cudaMemcpyAsync(ctx->d_jobs2.p, jobs.data(), sizeof(PeqJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const int nj = (int)jobs.size();
+    k_build_peq<<<(nj + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_jobs2.as<PeqJob>(), nj, ctx->d_codes.as<unsigned char>(), ctx->d_peq2.as<u64>());
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return 0;
+}
+
+// Score-only BandEd passes for host-built tasks (tables in d_peq2).  Leaves the exported state / scores / BandOut
+// resident for a following combine.  tasks[i].slot = i.
+int run_score_tasks(qb200_ctx *ctx, std::vector<BandTask> &tasks, std::vector<BandOut> &outs, int stage)
+{
+    const size_t nt = tasks.size();
+    outs.resize(nt);
+    if (!nt) return 0;
+    i64 st = 0, sc = 0;
+    unsigned mask = 0;
+    for (size_t i = 0; i < nt; ++i) {
+        BandTask &t = tasks[i];
+        const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
+        const int R = rounds_for(g.Bs);
+        if (!R) { ctx->err = "score-only band of " + std::to_string(g.Bs) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
+        mask |= (unsigned)R;
+        t.slot = (int)i; t.state_off = st; t.scores_off = sc;
+        st += 2 * g.Bs; sc += (i64)((t.m + 63) / 64) + g.Bs + 2;
+    }
+    CK(ctx->d_state.reserve((size_t)st * 8 + 16));
+    CK(ctx->d_scores.reserve((size_t)sc * 4 + 16));
+    CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)sc * 4, ctx->stream));
+    CK(ctx->d_bandout.reserve(sizeof(BandOut) * nt));
+    CK(ctx->d_tasks2.reserve(sizeof(BandTask) * nt));
+    CK(cudaMemcpyAsync(ctx->d_tasks2.p, tasks.data(), sizeof(BandTask) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Span sp(ctx, stage);
+        int rc = launch_banded<false>(ctx, mask, ctx->d_tasks2.as<BandTask>(), nullptr, 0, (int)nt, 0, ctx->d_peq2.as<u64>());
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(outs.data(), ctx->d_bandout.p, sizeof(BandOut) * nt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int run_win_tasks(qb200_ctx *ctx, std::vector<WinTask> &tasks, std::vector<WinOut> &outs, int stage)
+{
+    const size_t nt = tasks.size();
+    outs.resize(nt);
+    if (!nt) return 0;
+    i64 scr = 0;
+    for (size_t i = 0; i < nt; ++i) { tasks[i].slot = (int)i; tasks[i].scratch_off = scr; scr += (i64)(64 * tasks[i].W + 3) * tasks[i].W; }
+    CK(ctx->d_winscratch.reserve((size_t)scr * 16 + 64));
+    CK(ctx->d_wintasks.reserve(sizeof(WinTask) * nt));
+    CK(ctx->d_winout.reserve(sizeof(WinOut) * nt));
+    CK(cudaMemcpyAsync(ctx->d_wintasks.p, tasks.data(), sizeof(WinTask) * nt, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Span sp(ctx, stage);
+        k_windowed_warp<<<(int)((nt + 3) / 4), 128, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                                                                       ctx->d_peq2.as<u64>(), ctx->d_winscratch.as<ulonglong2>(), ctx->d_ops.as<u32>(),
+                                                                       ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>());
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    CK(cudaMemcpyAsync(outs.data(), ctx->d_winout.p, sizeof(WinOut) * nt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Full-matrix fill + traceback of host-built leaves that already sit in d_leaves[L0 .. L0+leaves.size()).
+int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
+{
+    const size_t nl = leaves.size();
+    if (!nl) return 0;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, (size_t)((free_b + ctx->d_matrix.cap) * 0.85)) / 16);
+    std::vector<int> Bc(nl), list_t, list_w;
+    i64 rg = 0, sc = 0;
+    for (size_t i = 0; i < nl; ++i) {
+        BandTask &t = leaves[i];
+        const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
+        Bc[i] = (int)g.Bc;
+        if (g.Bc > kThreadBandMax && !rounds_for(g.Bc)) { ctx->err = "leaf band of " + std::to_string(g.Bc) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
+        (g.Bc <= kThreadBandMax ? list_t : list_w).push_back((int)i);
+        t.range_off = rg; rg += t.n / 64 + 2;
+        t.scores_off = sc; if (g.Bc > kThreadBandMax) sc += (i64)((t.m + 63) / 64) + g.Bc + 2;
+    }
+    // chunk plans: (is_thread, list begin, list end, entries)
+    struct Chunk { int thr, q0, q1; i64 ent; };
+    std::vector<Chunk> chunks;
+    for (size_t g0 = 0; g0 < list_t.size();) {                       // thread-kernel groups of 32
+        i64 ent = 0; size_t q0 = g0;
+        while (g0 < list_t.size()) {
+            const size_t g1 = std::min(list_t.size(), g0 + 32);
+            int Bg = 1, nmax = 1;
+            for (size_t q = g0; q < g1; ++q) { Bg = std::max(Bg, Bc[list_t[q]]); nmax = std::max(nmax, leaves[list_t[q]].n); }
+            const i64 gent = (i64)(nmax + 1) * Bg * 32;
+            if (g0 > q0 && ent + gent > limit) break;
+            for (size_t q = g0; q < g1; ++q) { BandTask &t = leaves[list_t[q]]; t.mat_off = ent + (i64)(q - g0); t.mat_cs = Bg * 32; t.mat_ws = 32; }
+            ent += gent; g0 = g1;
+        }
+        chunks.push_back({1, (int)q0, (int)g0, ent});
+    }
+    for (size_t q0 = 0; q0 < list_w.size();) {                        // warp-kernel leaves
+        i64 ent = 0; size_t q1 = q0;
+        while (q1 < list_w.size()) {
+            BandTask &t = leaves[list_w[q1]];
+            const i64 e = (i64)(t.n + 1) * Bc[list_w[q1]];
+            if (q1 > q0 && ent + e > limit) break;
+            t.mat_off = ent; t.mat_cs = Bc[list_w[q1]]; t.mat_ws = 1;
+            ent += e; ++q1;
+        }
+        if ((size_t)ent * 16 > free_b + ctx->d_matrix.cap) { ctx->err = "a single traceback matrix does not fit the device"; return QB200_ERR_OOM; }
+        chunks.push_back({0, (int)q0, (int)q1, ent});
+        q0 = q1;
+    }
+    for (int &v : list_t) v += (int)L0;
+    for (int &v : list_w) v += (int)L0;
+    CK(cudaMemcpyAsync(ctx->d_leaves.as<BandTask>() + L0, leaves.data(), sizeof(BandTask) * nl, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_list_t.reserve(list_t.size() * 4 + 16));
+    CK(ctx->d_list_w.reserve(list_w.size() * 4 + 16));
+    CK(cudaMemcpyAsync(ctx->d_list_t.p, list_t.data(), list_t.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_list_w.p, list_w.data(), list_w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_ranges.reserve((size_t)rg * 8 + 16));
+    CK(ctx->d_scores.reserve((size_t)sc * 4 + 16));
+    CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)sc * 4 + 16, ctx->stream));
+    for (const Chunk &c : chunks) {
+        CK(ctx->d_matrix.reserve((size_t)c.ent * 16));
+        const int *lst = c.thr ? ctx->d_list_t.as<int>() : ctx->d_list_w.as<int>();
+        {
+            Span sp(ctx, ST_FILL);
+            int rc = c.thr ? launch_thread_fill(ctx, lst, c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>())
+                           : launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), lst, c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>());
+            if (rc) return rc;
+        }
+        {
+            Span sp(ctx, ST_TRACE);
+            int rc = launch_traceback(ctx, lst, c.q0, c.q1 - c.q0, 0);
+            if (rc) return rc;
+        }
+        ctx->stats.matrix_bytes += c.ent * 16;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->stats.leaves += (i64)nl;
+    return 0;
+}
+
+}  // namespace
+
 static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std::vector<int> &slow_pairs,
                          i64 &n_leaves_total, i64 &ops_words_total, i64 &range_total, std::vector<PairLeaves> &slow_pl)
 {
-    // Not implemented yet: the pairs keep QUICKED_UNIMPLEMENTED so the caller sees a loud, per-pair error.
-    (void)prm; (void)n_leaves_total; (void)ops_words_total; (void)range_total; (void)slow_pl;
-    std::vector<int> st(slow_pairs.size(), (int)QUICKED_UNIMPLEMENTED);
-    for (size_t q = 0; q < slow_pairs.size(); ++q)
-        CK(cudaMemcpyAsync(ctx->d_status.as<int>() + slow_pairs[q], &st[q], 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stats.pairs_stage2 += (i64)slow_pairs.size();
+    (void)range_total;
+    const size_t ns = slow_pairs.size();
+    const i64 n = ctx->n_pairs;
+    std::vector<SlowResult> res(ns);
+    for (size_t q = 0; q < ns; ++q) {
+        res[q].pair = slow_pairs[q]; res[q].status = QUICKED_ERROR; res[q].score = -1; res[q].set_score = 0;
+        res[q].pl.first_leaf = 0; res[q].pl.n_leaves = 0; res[q].pl.pad_ = 0;
+    }
+    const int W = (int)prm.window_size, O = (int)prm.overlap_size;
+    const bool sse = !prm.force_scalar;
+    std::vector<i64> cutoff(ns, 0);
+    std::vector<char> align(ns, 0);        // goes on to the Hirschberg stage
+    const int ok_status = (prm.algo == HIRSCHBERG) ? QUICKED_OK : QUICKED_WIP;
+    const i64 L0 = n_leaves_total;
+    std::vector<BandTask> leaves;          // appended leaves (incl. WINDOWED pseudo-leaves), global index L0 + k
+    i64 ops_words = ops_words_total;
+
+    auto pair_of = [&](size_t q) -> const PairRec & { return ctx->h_pairs[(size_t)slow_pairs[q]]; };
+
+    if (prm.algo == WINDOWED) {                                             // run_windowed, quicked.c:91-123
+        std::vector<PeqJob> jobs;
+        std::vector<WinTask> wt;
+        std::vector<size_t> who;
+        for (size_t q = 0; q < ns; ++q) {
+            const PairRec &r = pair_of(q);
+            if (W < 1 || W > 32 || O < 0 || O >= W) { res[q].status = QUICKED_UNIMPLEMENTED; continue; }
+            PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = 0;
+            jobs.push_back(j);
+            WinTask t{};
+            t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = 0; t.W = W; t.O = O; t.hew_threshold = 0;
+            t.sse = sse; t.score_only = prm.only_score; t.nbp = (r.m + 63) / 64 + 2;
+            if (!prm.only_score) {
+                BandTask lf{};
+                lf.p_off = r.p_off; lf.t_off = r.t_off; lf.m = r.m; lf.n = r.n; lf.pair = slow_pairs[q];
+                lf.ops_cap = ((r.m + r.n + 15) / 16) * 16; lf.ops_off = ops_words; ops_words += lf.ops_cap / 16;
+                lf.slot = (int)(L0 + (i64)leaves.size());
+                t.ops_off = lf.ops_off; t.ops_cap = lf.ops_cap; t.leaf_slot = lf.slot;
+                res[q].pl.first_leaf = lf.slot; res[q].pl.n_leaves = 1;
+                leaves.push_back(lf);
+            }
+            wt.push_back(t); who.push_back(q);
+        }
+        int rc = build_tables(ctx, jobs);
+        if (rc) return rc;
+        for (size_t k = 0; k < wt.size(); ++k) wt[k].peq_off = jobs[k].peq_off;
+        CK(ctx->d_ops.grow_keep((size_t)std::max<i64>(ops_words, 1) * 4 + 16, (size_t)ops_words_total * 4, ctx->stream));
+        CK(ctx->d_leaves.grow_keep(sizeof(BandTask) * (size_t)std::max<i64>(L0 + (i64)leaves.size(), 1), sizeof(BandTask) * (size_t)L0, ctx->stream));
+        CK(ctx->d_leafout.grow_keep(sizeof(LeafOut) * (size_t)std::max<i64>(L0 + (i64)leaves.size(), 1), sizeof(LeafOut) * (size_t)L0, ctx->stream));
+        if (!leaves.empty())
+            CK(cudaMemcpyAsync(ctx->d_leaves.as<BandTask>() + L0, leaves.data(), sizeof(BandTask) * leaves.size(), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<WinOut> wo;
+        rc = run_win_tasks(ctx, wt, wo, ST_WL);
+        if (rc) return rc;
+        for (size_t k = 0; k < wt.size(); ++k) {
+            const size_t q = who[k];
+            res[q].status = QUICKED_WIP;
+            if (prm.only_score) { res[q].score = wo[k].score; res[q].set_score = 1; }
+        }
+        n_leaves_total = L0 + (i64)leaves.size();
+        ops_words_total = ops_words;
+    } else if (prm.algo == BANDED) {                                        // BANDED only_score (run_banded with SCORE_ONLY)
+        std::vector<PeqJob> jobs;
+        std::vector<BandTask> bt;
+        for (size_t q = 0; q < ns; ++q) {
+            const PairRec &r = pair_of(q);
+            PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = 0;
+            jobs.push_back(j);
+            BandTask t{};
+            t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = 0; t.finish = r.n;
+            t.cutoff = (i64)((unsigned)std::max(r.m, r.n) * prm.bandwidth / 100);
+            t.nbp = (r.m + 63) / 64 + 2; t.pair = slow_pairs[q];
+            bt.push_back(t);
+        }
+        int rc = build_tables(ctx, jobs);
+        if (rc) return rc;
+        for (size_t k = 0; k < bt.size(); ++k) bt[k].peq_off = jobs[k].peq_off;
+        std::vector<BandOut> bo;
+        rc = run_score_tasks(ctx, bt, bo, ST_BANDED);
+        if (rc) return rc;
+        for (size_t q = 0; q < ns; ++q) { res[q].status = QUICKED_WIP; res[q].score = bo[q].score; res[q].set_score = 1; }
+        ctx->stats.banded_tries += (i64)ns;
+    } else {
+        // ---------------- QUICKED stages 2-3 (quicked.c:201-280) / HIRSCHBERG cutoffs ----------------
+        if (prm.algo == QUICKED) {
+            std::vector<int> hb((size_t)n), hh((size_t)n);
+            CK(cudaMemcpyAsync(hb.data(), ctx->d_bound.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hh.data(), ctx->d_hew.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            std::vector<size_t> s2;
+            for (size_t q = 0; q < ns; ++q) {
+                const PairRec &r = pair_of(q);
+                const unsigned maxlen = (unsigned)std::max(r.m, r.n);
+                cutoff[q] = hb[(size_t)slow_pairs[q]];
+                align[q] = 1;
+                if ((i64)hh[(size_t)slow_pairs[q]] * 64 > (i64)(maxlen * prm.hew_percentage[0] / 100)) s2.push_back(q);
+            }
+            ctx->stats.pairs_stage2 += (i64)s2.size();
+            if (!s2.empty() && (W < 1 || W > 32 || O < 0 || O >= W)) {
+                for (size_t q : s2) { res[q].status = QUICKED_UNIMPLEMENTED; align[q] = 0; }
+                s2.clear();
+            }
+            std::vector<size_t> s3;
+            if (!s2.empty()) {
+                std::vector<PeqJob> jobs;
+                std::vector<WinTask> wt;
+                for (size_t q : s2) {
+                    const PairRec &r = pair_of(q);
+                    for (int rev = 0; rev < 2; ++rev) {
+                        PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = rev; j.peq_off = 0;
+                        jobs.push_back(j);
+                        WinTask t{};
+                        t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = rev; t.W = W; t.O = O;
+                        t.hew_threshold = (int)prm.hew_threshold[1]; t.sse = sse; t.score_only = 1; t.nbp = (r.m + 63) / 64 + 2;
+                        wt.push_back(t);
+                    }
+                }
+                int rc = build_tables(ctx, jobs);
+                if (rc) return rc;
+                for (size_t k = 0; k < wt.size(); ++k) wt[k].peq_off = jobs[k].peq_off;
+                std::vector<WinOut> wo;
+                rc = run_win_tasks(ctx, wt, wo, ST_WL);
+                if (rc) return rc;
+                for (size_t k = 0; k < s2.size(); ++k) {
+                    const size_t q = s2[k];
+                    const PairRec &r = pair_of(q);
+                    const unsigned maxlen = (unsigned)std::max(r.m, r.n);
+                    i64 score = wo[2 * k].score;                                   // quicked.c:213-230
+                    unsigned long long hewv = (unsigned long long)wo[2 * k].hew;
+                    score = std::min<i64>(score, wo[2 * k + 1].score);
+                    if (score >= wo[2 * k + 1].score) hewv = (unsigned long long)wo[2 * k + 1].hew;
+                    cutoff[q] = score;
+                    if (hewv * 64ull * (unsigned long long)(prm.window_size - prm.overlap_size) >
+                        (unsigned long long)(maxlen * prm.hew_percentage[1] / 100)) s3.push_back(q);   // :237-238
+                }
+            }
+            ctx->stats.pairs_stage3 += (i64)s3.size();
+            if (!s3.empty()) {                                                     // band doubling, quicked.c:240-278
+                std::vector<PeqJob> jobs;
+                for (size_t q : s3) {
+                    const PairRec &r = pair_of(q);
+                    PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = 0;
+                    jobs.push_back(j);
+                    const i64 bw = (i64)((unsigned)std::max(r.m, r.n) * prm.bandwidth / 100);
+                    cutoff[q] = std::min<i64>(bw, cutoff[q]);                      // :246
+                }
+                int rc = build_tables(ctx, jobs);
+                if (rc) return rc;
+                std::vector<size_t> active(s3.size());
+                for (size_t k = 0; k < s3.size(); ++k) active[k] = k;
+                while (!active.empty()) {
+                    std::vector<BandTask> bt;
+                    for (size_t k : active) {
+                        const size_t q = s3[k];
+                        const PairRec &r = pair_of(q);
+                        BandTask t{};
+                        t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = 0; t.finish = r.n;
+                        t.cutoff = cutoff[q]; t.peq_off = jobs[k].peq_off; t.nbp = (r.m + 63) / 64 + 2; t.pair = slow_pairs[q];
+                        bt.push_back(t);
+                    }
+                    std::vector<BandOut> bo;
+                    rc = run_score_tasks(ctx, bt, bo, ST_BANDED);
+                    if (rc) return rc;
+                    ctx->stats.banded_tries += (i64)bt.size();
+                    std::vector<size_t> next;
+                    for (size_t a = 0; a < active.size(); ++a) {
+                        const size_t q = s3[active[a]];
+                        const PairRec &r = pair_of(q);
+                        const i64 nw = bo[a].score, maxlen = std::max(r.m, r.n);
+                        if ((nw > maxlen / 4 && cutoff[q] * 3 / 2 < nw) || nw < 0) { cutoff[q] *= 2; next.push_back(active[a]); }   // :260-263
+                        else cutoff[q] = nw;                                        // :278
+                    }
+                    active.swap(next);
+                }
+            }
+        } else {   // HIRSCHBERG
+            for (size_t q = 0; q < ns; ++q) {
+                const PairRec &r = pair_of(q);
+                cutoff[q] = (i64)((unsigned)std::max(r.m, r.n) * prm.bandwidth / 100);   // quicked.c:131
+                align[q] = 1;
+            }
+        }
+
+        // ---------------- Hirschberg: level-synchronous split tree (bpm_hirschberg.c:33-270) ----------------
+        std::vector<HNode> cur, leaf_nodes;
+        std::vector<char> bad(ns, 0);
+        std::vector<i64> fail_t(ns, -1);          // largest t_off of a non-converging node (DFS-first failure)
+        std::vector<int> q_of_pair_local;         // node.pair holds the LOCAL slow index q
+        for (size_t q = 0; q < ns; ++q) {
+            if (!align[q]) continue;
+            const PairRec &r = pair_of(q);
+            cur.push_back({(int)q, r.p_off, r.t_off, r.m, r.n, cutoff[q]});
+        }
+        while (!cur.empty()) {
+            std::vector<HNode> splits;
+            for (const HNode &nd : cur) {
+                const BandGeom g = band_geometry(nd.m, nd.n, nd.cutoff);
+                if ((unsigned long long)g.Bc * (unsigned long long)nd.n * 16ull > (1ull << 24)) {
+                    if (!rounds_for(g.Bs)) { bad[(size_t)nd.pair] = 2; continue; }
+                    splits.push_back(nd);
+                } else leaf_nodes.push_back(nd);
+            }
+            cur.clear();
+            if (splits.empty()) break;
+            ctx->stats.hirschberg_splits += (i64)splits.size();
+            std::vector<PeqJob> jobs;
+            std::vector<BandTask> bt;
+            for (const HNode &nd : splits) {
+                const int n_l = (nd.n + 1) / 2;
+                for (int rev = 0; rev < 2; ++rev) {
+                    PeqJob j; j.src_off = nd.p_off; j.m = nd.m; j.rev = rev; j.peq_off = 0;
+                    jobs.push_back(j);
+                    BandTask t{};
+                    t.p_off = nd.p_off; t.t_off = nd.t_off; t.m = nd.m; t.n = nd.n; t.rev = rev;
+                    t.finish = rev ? nd.n - n_l : n_l; t.cutoff = nd.cutoff; t.nbp = (nd.m + 63) / 64 + 2; t.pair = nd.pair;
+                    bt.push_back(t);
+                }
+            }
+            int rc = build_tables(ctx, jobs);
+            if (rc) return rc;
+            for (size_t k = 0; k < bt.size(); ++k) bt[k].peq_off = jobs[k].peq_off;
+            std::vector<BandOut> bo;
+            rc = run_score_tasks(ctx, bt, bo, ST_FILL);
+            if (rc) return rc;
+            std::vector<SplitTask> stv(splits.size());
+            i64 scr = 0;
+            for (size_t k = 0; k < splits.size(); ++k) {
+                const BandGeom g = band_geometry(splits[k].m, splits[k].n, splits[k].cutoff);
+                SplitTask &s = stv[k];
+                s.m = splits[k].m; s.n = splits[k].n; s.cutoff = splits[k].cutoff;
+                s.fwd_slot = (int)(2 * k); s.rev_slot = (int)(2 * k + 1);
+                s.fwd_state = bt[2 * k].state_off; s.rev_state = bt[2 * k + 1].state_off;
+                s.fwd_scores = bt[2 * k].scores_off; s.rev_scores = bt[2 * k + 1].scores_off;
+                s.scratch_off = scr; scr += 2 * (64 * g.Bs + 8);
+            }
+            CK(ctx->d_split.reserve(sizeof(SplitTask) * stv.size()));
+            CK(ctx->d_splitout.reserve(sizeof(SplitOut) * stv.size()));
+            CK(ctx->d_splitscratch.reserve((size_t)scr * 4 + 64));
+            CK(cudaMemcpyAsync(ctx->d_split.p, stv.data(), sizeof(SplitTask) * stv.size(), cudaMemcpyHostToDevice, ctx->stream));
+            k_hirschberg_combine<<<(int)((stv.size() + 63) / 64), 64, 0, ctx->stream>>>(ctx->d_split.as<SplitTask>(), (int)stv.size(), ctx->d_bandout.as<BandOut>(),
+                ctx->d_state.as<u64>(), ctx->d_scores.as<int>(), ctx->d_splitscratch.as<int>(), ctx->d_splitout.as<SplitOut>());
+            CK(cudaGetLastError());
+            ctx->stats.kernel_launches++;
+            std::vector<SplitOut> so(stv.size());
+            CK(cudaMemcpyAsync(so.data(), ctx->d_splitout.p, sizeof(SplitOut) * so.size(), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (size_t k = 0; k < splits.size(); ++k) {
+                const HNode &nd = splits[k];
+                if (so[k].status == -2) { fail_t[(size_t)nd.pair] = std::max(fail_t[(size_t)nd.pair], nd.t_off); continue; }
+                if (so[k].status != 0) { bad[(size_t)nd.pair] = 1; continue; }
+                const int n_l = (nd.n + 1) / 2, m_l = so[k].m_l;
+                cur.push_back({nd.pair, nd.p_off + m_l, nd.t_off + n_l, nd.m - m_l, nd.n - n_l, so[k].score_r});   // right first (:212-222)
+                cur.push_back({nd.pair, nd.p_off, nd.t_off, m_l, n_l, so[k].score_l});
+            }
+        }
+        // leaves, left to right per pair; after a non-converging node only the leaves to its right were emitted
+        std::stable_sort(leaf_nodes.begin(), leaf_nodes.end(), [](const HNode &a, const HNode &b) {
+            return a.pair != b.pair ? a.pair < b.pair : a.t_off < b.t_off; });
+        std::vector<PeqJob> jobs;
+        for (const HNode &nd : leaf_nodes) {
+            const size_t q = (size_t)nd.pair;
+            if (bad[q]) continue;
+            if (fail_t[q] >= 0 && nd.t_off <= fail_t[q]) continue;
+            PeqJob j; j.src_off = nd.p_off; j.m = nd.m; j.rev = 0; j.peq_off = 0;
+            jobs.push_back(j);
+            BandTask lf{};
+            lf.p_off = nd.p_off; lf.t_off = nd.t_off; lf.m = nd.m; lf.n = nd.n; lf.rev = 0; lf.finish = nd.n; lf.cutoff = nd.cutoff;
+            lf.nbp = (nd.m + 63) / 64 + 2; lf.pair = slow_pairs[q];
+            lf.ops_cap = ((nd.m + nd.n + 15) / 16) * 16; lf.ops_off = ops_words; ops_words += lf.ops_cap / 16;
+            lf.slot = (int)(L0 + (i64)leaves.size());
+            if (res[q].pl.n_leaves == 0) res[q].pl.first_leaf = lf.slot;
+            res[q].pl.n_leaves++;
+            if (res[q].pl.n_leaves > 1) ctx->multi_leaf_pairs = true;
+            leaves.push_back(lf);
+        }
+        for (size_t q = 0; q < ns; ++q) {
+            if (!align[q]) continue;
+            if (bad[q] == 2) res[q].status = QUICKED_UNIMPLEMENTED;
+            else if (bad[q]) res[q].status = QUICKED_ERROR;
+            else if (fail_t[q] >= 0 && prm.algo == HIRSCHBERG) res[q].status = QUICKED_FAIL_NON_CONVERGENCE;   // quicked.c:160
+            else res[q].status = ok_status;                                                                   // QUICKED ignores it (:290)
+            if (!bad[q] && res[q].pl.n_leaves == 0) { res[q].score = 0; res[q].set_score = 1; }               // empty op list
+        }
+        int rc = build_tables(ctx, jobs);
+        if (rc) return rc;
+        for (size_t k = 0; k < leaves.size(); ++k) leaves[k].peq_off = jobs[k].peq_off;
+        CK(ctx->d_ops.grow_keep((size_t)std::max<i64>(ops_words, 1) * 4 + 16, (size_t)ops_words_total * 4, ctx->stream));
+        CK(ctx->d_leaves.grow_keep(sizeof(BandTask) * (size_t)std::max<i64>(L0 + (i64)leaves.size(), 1), sizeof(BandTask) * (size_t)L0, ctx->stream));
+        CK(ctx->d_leafout.grow_keep(sizeof(LeafOut) * (size_t)std::max<i64>(L0 + (i64)leaves.size(), 1), sizeof(LeafOut) * (size_t)L0, ctx->stream));
+        CK(ctx->d_bandout.reserve(sizeof(BandOut) * (size_t)std::max<i64>(L0 + (i64)leaves.size(), 1)));
+        rc = run_leaves_host(ctx, leaves, L0);
+        if (rc) return rc;
+        n_leaves_total = L0 + (i64)leaves.size();
+        ops_words_total = ops_words;
+    }
+    // scatter per-pair results
+    CK(ctx->d_scatter.reserve(sizeof(SlowResult) * ns));
+    CK(cudaMemcpyAsync(ctx->d_scatter.p, res.data(), sizeof(SlowResult) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    k_scatter_slow<<<(int)((ns + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_scatter.as<SlowResult>(), (int)ns, ctx->d_pairleaves.as<PairLeaves>(),
+                                                                      ctx->d_status.as<int>(), ctx->d_score.as<int>());
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    CK(cudaStreamSynchronize(ctx->stream));     // `res` is on the host stack
+    slow_pl.clear();
     return 0;
 }
 

@@ -42,7 +42,7 @@ struct PlanParams {
 
 __device__ __forceinline__ int rounds_for_dev(i64 B)
 {
-    return B <= 32 ? 1 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : B <= 1024 ? 32 : 0;
+    return B <= 32 ? 1 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : B <= 1024 ? 32 : B <= 11000 ? 64 : 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -183,6 +183,18 @@ k_merge_text_len(const int *__restrict__ text_len, i64 *__restrict__ text_bytes,
 __global__ void k_last_offset(const i64 *__restrict__ offs, const i64 *__restrict__ vals, int n, i64 *out, i64 *offs_n)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) { const i64 t = offs[n - 1] + vals[n - 1]; out[0] = t; offs_n[0] = t; }
+}
+
+// Results of the host-driven path scattered back into the per-pair arrays.
+struct SlowResult { int pair; int status; int score; int set_score; PairLeaves pl; };
+__global__ void __launch_bounds__(256)
+k_scatter_slow(const SlowResult *__restrict__ res, int n, PairLeaves *__restrict__ pl, int *__restrict__ status, int *__restrict__ score)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const SlowResult r = res[q];
+    pl[r.pair] = r.pl; status[r.pair] = r.status;
+    if (r.set_score) score[r.pair] = r.score;
 }
 
 }  // namespace qb

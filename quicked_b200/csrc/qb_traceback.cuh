@@ -73,10 +73,15 @@ k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ l
     while (v >= 0 && h >= 0) {
         const int ev = v - 64 * ((h >> 6) - prolog);
         const int evr = v - 64 * (((h + 1) >> 6) - prolog);
-        const int wr = evr >> 6, wl = ev >> 6;
+        // word numbers with C truncation (the reference divides a possibly negative row offset, bpm_banded.c:995-998)
+        int wr = evr / 64, wl = ev / 64, cr = h + 1, cl = h;
+        // a row outside the band's coordinates makes the reference index the flat [column][word] array across
+        // column boundaries; follow the same flat index (only possible when the band is too narrow)
+        if (wr < 0 || wr >= B) { const i64 f = (i64)cr * B + wr; cr = f >= 0 ? (int)(f / B) : -1; wr = f >= 0 ? (int)(f % B) : -1; }
+        if (wl < 0 || wl >= B) { const i64 f = (i64)cl * B + wl; cl = f >= 0 ? (int)(f / B) : -1; wl = f >= 0 ? (int)(f % B) : -1; }
         u64 pvw = 0, mvw = 0;
-        if (cell_written(ranges, B, h + 1, wr)) pvw = mat[(i64)(h + 1) * tk.mat_cs + (i64)wr * tk.mat_ws].x;
-        if (cell_written(ranges, B, h, wl)) mvw = mat[(i64)h * tk.mat_cs + (i64)wl * tk.mat_ws].y;
+        if (cr >= 0 && cr <= tk.n && cell_written(ranges, B, cr, wr)) pvw = mat[(i64)cr * tk.mat_cs + (i64)wr * tk.mat_ws].x;
+        if (cl >= 0 && cl <= tk.n && cell_written(ranges, B, cl, wl)) mvw = mat[(i64)cl * tk.mat_cs + (i64)wl * tk.mat_ws].y;
         if ((pvw >> (evr & 63)) & 1ull) { w.emit(OP_D); --v; }
         else if ((mvw >> (ev & 63)) & 1ull) { w.emit(OP_I); --h; }
         else { w.emit(traw[h] == praw[v] ? OP_M : OP_X); --h; --v; }

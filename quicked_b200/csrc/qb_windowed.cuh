@@ -11,9 +11,10 @@
 //
 // SSE=true reproduces the observable behaviour of windowed_compute_window_sse (bpm_windowed.c:283-445), which is
 // what the reference runs on x86 unless force_scalar is set (dispatch :577); SSE=false follows the scalar
-// windowed_compute_window (:202-280).  The differences are listed in SURVEY.md App. A.4 and oracle/quicked_oracle.c.
+// windowed_compute_window (:202-280).  The differences are listed in SURVEY.md App. A.4 and DESIGN.md.
 #pragma once
 #include "qb_common.cuh"
+#include "qb_traceback.cuh"
 
 namespace qb {
 
@@ -121,6 +122,155 @@ k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigne
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ws += __shfl_down_sync(kFull, ws, o);
     if ((t & 31) == 0 && ws) atomicAdd(&counters[0], ws);
+}
+
+
+// ----------------------------------------------------------------------------------------------------------------
+// k_windowed_warp: WindowEd for ANY window / overlap (W <= 32 words), score-only or CIGAR mode, forward or
+// reversed sequences.  ONE PAIR PER WARP, one window word per lane, all lanes on the same column with the same
+// ballot carry-lookahead as k_banded_warp (the window has no band bookkeeping: reference bpm_windowed.c:202-280).
+// The filled window (64W+2 columns x W words of (Pv,Mv)) goes to a per-warp scratch in HBM/L2 exactly as the
+// reference stores it (bpm_windowed.c:143); lane 0 then walks it (bpm_windowed.c:448-561).
+// Used by: QUICKED stage 2 (WindowEd(L) forward and reverse, quicked.c:204-233), the WINDOWED algorithm
+// (quicked.c:91-123).  For W == 2 and !force_scalar the SSE variant's quirks are reproduced (see k_windowed21_score).
+struct WinTask {
+    i64 p_off, t_off;      // pattern / text start in the packed buffer (forward coordinates)
+    int m, n;
+    int rev;               // 1: run on the reversed sequences
+    int W, O;
+    int hew_threshold;
+    int sse;               // emulate windowed_compute_window_sse (only when W == 2)
+    int score_only;
+    i64 peq_off; int nbp;  // match masks of the (possibly reversed) pattern
+    int slot;              // output index
+    i64 scratch_off;       // ulonglong2 index of this warp's window scratch ((64W+3)*W entries)
+    i64 ops_off; int ops_cap;   // CIGAR mode: op region
+    int leaf_slot;              // CIGAR mode: index of the pseudo-leaf's LeafOut
+};
+struct WinOut { int score; int hew; };
+
+__global__ void __launch_bounds__(128)
+k_windowed_warp(const WinTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ codes,
+                const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, ulonglong2 *__restrict__ scratch,
+                u32 *__restrict__ ops_pool, WinOut *__restrict__ outs, LeafOut *__restrict__ leaf_outs,
+                u64 *__restrict__ counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (id >= n_tasks) return;
+    const WinTask tk = tasks[id];
+    const int W = tk.W, O = tk.O;
+    const u64 *pq = peq + tk.peq_off;
+    const unsigned char *tc = codes + tk.t_off, *traw = raw + tk.t_off, *praw = raw + tk.p_off;
+    ulonglong2 *win = scratch + tk.scratch_off;                 // [column][word]
+    const bool sse = tk.sse && W == 2;
+    OpWriter ow;
+    if (!tk.score_only && lane == 0) ow.init(ops_pool + tk.ops_off, tk.ops_cap);
+    int cv = tk.m - 1, ch = tk.n - 1, score = 0, hew = 0;
+    u64 ws = 0;
+    const int hew_lim = (W - O) * 64 * tk.hew_threshold / 100;
+    while (cv >= 0 && ch >= 0) {
+        const int v0 = max(cv - 64 * W + 1, 0), h0 = max(ch - 64 * W + 1, 0);
+        const int words = ((cv - v0) >> 6) + 1, cols = ch - h0 + 1;
+        const bool act = lane < words;
+        // window-aligned match masks of this lane's word (bpm_windowed.c:237-244)
+        u64 eqw[kAlpha];
+        {
+            const unsigned sh = v0 & 63;
+            const int blk = (v0 >> 6) + lane;
+#pragma unroll
+            for (int c = 0; c < kAlpha; ++c) {
+                u64 e = 0;
+                if (act) e = funnel_r(pq[(i64)c * tk.nbp + blk], pq[(i64)c * tk.nbp + blk + 1], sh);
+                eqw[c] = e;
+            }
+        }
+        u64 pv = (h0 == 0) ? ~0ull : 0ull, mv = 0;
+        if (lane < W) win[lane] = make_ulonglong2(pv, 0ull);   // column 0 (bpm_windowed.c:225-229)
+        const u32 top_in = (v0 == 0);
+        u64 pv_prev = 0, mv_prev = 0;
+        const int ncol = (sse && words == 2 && !(cols & 1)) ? cols + 1 : cols;   // + SSE look-ahead column
+        for (int c = 0; c < ncol; ++c) {
+            const bool la = c >= cols;                           // look-ahead pass: lane 0 = column `cols`, lane 1 redoes column cols-1
+            int col_t = h0 + c;
+            if (la && lane == 1) col_t = h0 + cols - 1;
+            int code = 4;
+            if (col_t < tk.n) code = tk.rev ? tc[tk.n - 1 - col_t] : tc[col_t];
+            if (sse && c == cols - 1) { pv_prev = pv; mv_prev = mv; }
+            if (la && lane == 1) { pv = pv_prev; mv = mv_prev; }
+            u64 eq = eqw[0];
+#pragma unroll
+            for (int k = 1; k < kAlpha; ++k) if (code == k) eq = eqw[k];
+            u32 hp_top = top_in;
+            if (sse && c > 0) hp_top = (c == 1) | ((c & 1) ^ 1);
+            const u64 a = eq & pv, s = a + pv;
+            const u32 G = __ballot_sync(kFull, act && (s < a));
+            const u32 P = __ballot_sync(kFull, act && (s == ~0ull));
+            const u32 X = G | P;
+            u32 carries = (X + G) ^ X ^ G;                       // carry into lane l (top MHin = 0)
+            u32 my_c = (carries >> lane) & 1u;
+            if (sse && cols == 1 && lane == 1) my_c = 0;         // uninitialised carry in the reference (single-column window)
+            const u64 xh = ((s + my_c) ^ pv) | eq;
+            u64 ph = mv | ~(xh | pv);
+            u64 mh = pv & xh;
+            const u32 HP = __ballot_sync(kFull, (ph >> 63) != 0);
+            u32 hp_in = lane ? ((HP >> (lane - 1)) & 1u) : hp_top;
+            if (sse && cols == 1 && lane == 1) hp_in = 0;
+            ph = (ph << 1) | (u64)hp_in;
+            mh = (mh << 1) | (u64)my_c;
+            const u64 xv = eq | mv;
+            pv = mh | ~(xv | ph);
+            mv = ph & xv;
+            if (!la) { if (act) win[(i64)(c + 1) * W + lane] = make_ulonglong2(pv, mv); }
+            else if (lane == 1) win[(i64)cols * W + 1] = make_ulonglong2(pv, mv);
+        }
+        ws += (u64)words * cols;
+        __syncwarp();
+        // ---- walk (lane 0): D, I, M, X when score-only; M(raw) first, then D, I, X in CIGAR mode ----
+        int v = cv, h = ch;
+        if (lane == 0) {
+            const int v_stop = max(cv - 64 * (W - O) + 1, 0), h_stop = max(ch - 64 * (W - O) + 1, 0);
+            int cost = 0;
+            while (v >= v_stop && h >= h_stop) {
+                const int word = (v - v0) >> 6, bit = (v - v0) & 63;
+                const u64 dp = win[(i64)(h - h0 + 1) * W + word].x, im = win[(i64)(h - h0) * W + word].y;
+                const bool del = (dp >> bit) & 1ull, ins = (im >> bit) & 1ull;
+                const unsigned char tch = tk.rev ? traw[tk.n - 1 - h] : traw[h], pch = tk.rev ? praw[tk.m - 1 - v] : praw[v];
+                const bool same = tch == pch;
+                if (tk.score_only) {
+                    if (del) { ++cost; --v; }
+                    else if (ins) { ++cost; --h; }
+                    else { cost += !same; --h; --v; }
+                } else {
+                    if (same) { ow.emit(OP_M); --h; --v; }
+                    else if (del) { ow.emit(OP_D); --v; }
+                    else if (ins) { ow.emit(OP_I); --h; }
+                    else { ow.emit(OP_X); --h; --v; }
+                }
+            }
+            if (tk.score_only) { if (cost > hew_lim) ++hew; score += cost; }
+        }
+        cv = __shfl_sync(kFull, v, 0);
+        ch = __shfl_sync(kFull, h, 0);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (tk.score_only) {
+            if (ch >= 0) score += ch + 1;                        // bpm_windowed.c:599-607
+            if (cv >= 0) score += cv + 1;
+        } else {
+            for (int h = ch; h >= 0; --h) ow.emit(OP_I);         // :608-627
+            for (int v = cv; v >= 0; --v) ow.emit(OP_D);
+            ow.finish();
+            LeafOut o;
+            o.n_ops = tk.ops_cap - ow.pos; o.cost = ow.cost; o.text_len = ow.text_len; o.first_op = ow.cur_op; o.first_run = ow.cur_len;
+            leaf_outs[tk.leaf_slot] = o;
+            score = ow.cost;
+        }
+        WinOut wo; wo.score = score; wo.hew = hew;
+        outs[tk.slot] = wo;
+        atomicAdd(&counters[0], ws);
+    }
 }
 
 }  // namespace qb

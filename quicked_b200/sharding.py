@@ -1,0 +1,41 @@
+"""Multi-GPU sharding of a batch: contiguous index ranges per rank, no collective on the data path.
+
+The reference parallelises only across independent pairs (OpenMP `parallel for` over a batch,
+reference tools/align_benchmark/align_benchmark.c:269-284); the B200 equivalent is one process per GPU, each
+aligning its own contiguous slice, followed by a host-side gather of (score, CIGAR) back into input order."""
+
+
+def shard_range(n, rank, world):
+    """[lo, hi) of rank's contiguous slice; sizes differ by at most one"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_results(scores, cigars, rank, world):
+    """gather per-shard python lists on rank 0 in input order (torch.distributed object gather; gloo or nccl)"""
+    if world == 1:
+        return list(scores), list(cigars)
+    import torch.distributed as dist
+    out = [None] * world if rank == 0 else None
+    dist.gather_object((list(scores), list(cigars)), out, dst=0)
+    if rank != 0:
+        return None, None
+    all_s, all_c = [], []
+    for s, c in out:
+        all_s += s
+        all_c += c
+    return all_s, all_c
+
+
+def align_sharded(pairs, rank, world, device=None, **params):
+    """Align rank's slice of `pairs` on its GPU and gather everything on rank 0.  -> (status, score, cigar) list or None"""
+    from .capi import BatchAligner
+    lo, hi = shard_range(len(pairs), rank, world)
+    gpu = BatchAligner(device=rank if device is None else device)
+    res = gpu.align(pairs[lo:hi], **params)
+    gpu.close()
+    sc, cg = gather_results([(r[0], r[1]) for r in res], [r[2] for r in res], rank, world)
+    if rank != 0:
+        return None
+    return [(s[0], s[1], c) for s, c in zip(sc, cg)]

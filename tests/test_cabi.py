@@ -1,0 +1,101 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the headers declare, keeps the
+reference's struct layout, and refuses (loudly) to compute without a GPU.  No compute calls are made here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from _common import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from quicked_b200 import build as qbuild
+    qbuild.build()
+    from quicked_b200 import capi
+    return capi.load()
+
+
+def declared_symbols():
+    names = set()
+    for hdr in ("quicked.h", "quicked_b200.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b((?:quicked|qb200)_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_exports_every_declared_symbol(lib):
+    from quicked_b200 import capi
+    decl = declared_symbols()
+    assert {"quicked_new", "quicked_align", "quicked_free", "quicked_default_params", "quicked_check_error",
+            "quicked_status_msg", "qb200_align_batch"} <= decl
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert set(capi.EXPORTS) == decl
+
+
+def test_struct_layout_matches_reference():
+    """reference quicked.h:43-67 on x86-64: params 48 B, aligner 72 B"""
+    from quicked_b200 import capi
+    assert C.sizeof(capi.Params) == 48 and C.sizeof(capi.Aligner) == 72
+    assert capi.Params.hew_threshold.offset == 16 and capi.Params.only_score.offset == 32
+    assert capi.Params.external_allocator.offset == 40
+    assert capi.Aligner.cigar.offset == 16 and capi.Aligner.score.offset == 24 and capi.Aligner.timer.offset == 32
+
+
+def test_defaults_and_messages(lib):
+    from quicked_b200 import capi
+    p = lib.quicked_default_params()                      # reference quicked.c:308-321
+    assert (p.algo, p.bandwidth, p.window_size, p.overlap_size) == (0, 15, 9, 1)
+    assert list(p.hew_threshold) == [40, 40] and list(p.hew_percentage) == [15, 15]
+    assert not p.only_score and not p.force_scalar and not p.external_timer
+    assert lib.quicked_status_msg(-4).decode() == "ERROR: Tried to align an empty sequence\n"
+    assert lib.quicked_status_msg(1).decode() == "QuickEd finished without errors.\n"
+    assert lib.quicked_check_error(-1) and not lib.quicked_check_error(1) and not lib.quicked_check_error(0)
+    a = capi.Aligner()
+    assert lib.quicked_new(C.byref(a), C.byref(p)) == 1   # QUICKED_WIP
+    assert a.score == -1 and not a.cigar
+    assert lib.quicked_align(C.byref(a), b"", 0, b"", 0) == -4          # before any device work
+    p.algo = 17
+    assert lib.quicked_align(C.byref(a), b"ACGT", 4, b"ACGT", 4) == -3  # QUICKED_UNKNOWN_ALGO
+    assert lib.quicked_free(C.byref(a)) == 1
+
+
+def test_no_cpu_fallback(lib):
+    """without a GPU the product path must fail, not silently compute on the host"""
+    if lib.qb200_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    h = C.c_void_p()
+    assert lib.qb200_create(C.byref(h), 0) == -100          # QB200_ERR_NO_DEVICE
+    from quicked_b200 import capi
+    p = lib.quicked_default_params()
+    a = capi.Aligner()
+    lib.quicked_new(C.byref(a), C.byref(p))
+    assert lib.quicked_align(C.byref(a), b"ACGT", 4, b"ACTT", 4) == -1   # QUICKED_ERROR, message on stderr
+    assert a.score == -1
+    lib.quicked_free(C.byref(a))
+
+
+def test_product_never_touches_oracle():
+    """oracle/ is test infrastructure: nothing under quicked_b200/ or include/ may reference it"""
+    for base in ("quicked_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    assert "libqoracle" not in txt and "oracle.harness" not in txt and "quicked_oracle" not in txt, os.path.join(dp, f)
+
+
+def test_native_generator_model():
+    """seeded generate_dataset twin: text has exactly `length` bases, the pattern carries ceil(length*error) edits"""
+    from quicked_b200 import generate_pairs_native
+    seqs, po, pl, to, tl = generate_pairs_native(7, 200, 100, 0.05)
+    assert (tl == 100).all() and (abs(pl - 100) <= 5).all()
+    raw = seqs.tobytes()
+    assert set(raw[po[0]:po[0] + pl[0]]) <= set(b"ACGT")
+    seqs2, *_ = generate_pairs_native(7, 200, 100, 0.05)
+    assert (seqs == seqs2).all()
+    seqs3, *_ = generate_pairs_native(8, 200, 100, 0.05)
+    assert (seqs != seqs3).any()

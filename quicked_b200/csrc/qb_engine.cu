@@ -89,6 +89,7 @@ struct qb200_ctx {
     DevBuf d_leaves, d_leafout, d_pairleaves, d_work, d_bandout, d_matrix, d_scores, d_state, d_ops, d_ranges;
     DevBuf d_cls, d_cutoff, d_plan_items, d_plan_offs, d_textbytes, d_list_t, d_list_w, d_list_slow, d_gsize, d_goff, d_gB;
     unsigned char *h_pinned = nullptr;     // small pinned mailbox for totals
+    DevBuf d_quad;                         // WindowEd(S) quadrant scratch
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
     std::vector<int> h_score, h_status;
@@ -351,7 +352,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
                       &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
                       &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB, &ctx->d_peq2, &ctx->d_jobs2, &ctx->d_tasks2, &ctx->d_wintasks,
-                      &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter})
+                      &ctx->d_quad, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -491,18 +492,16 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     // ---- QUICKED stage 1: WindowEd(S) bound (quicked.c:178-199) ----
     if (prm.algo == QUICKED) {
         Span sp(ctx, ST_WS);
-        const int T = 64;
-        const size_t smem = (size_t)kWsSlots * T * 8;
-        const int blocks = (int)((n + T - 1) / T);
-        if (prm.force_scalar) {
-            CK(cudaFuncSetAttribute(k_windowed21_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_windowed21_score<false><<<blocks, T, smem, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>());
-        } else {
-            CK(cudaFuncSetAttribute(k_windowed21_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_windowed21_score<true><<<blocks, T, smem, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>());
-        }
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * kWsCtasPerSm);   // persistent: one wave
+        CK(ctx->d_quad.reserve((size_t)blocks * kWsThreads * kWsQuadSlots * 8));
+        if (prm.force_scalar)
+            k_windowed21_score<false><<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(), ctx->d_quad.as<u64>());
+        else
+            k_windowed21_score<true><<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(), ctx->d_quad.as<u64>());
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
     }

@@ -3,11 +3,10 @@
 // k_windowed21_score: the QUICKED stage-1 bound estimator, WindowEd(S) = 2-word windows overlapping by 1 word,
 // score only (reference quicked.c:178-199 -> bpm_windowed.c:563-628 with W=2, O=1, SCORE_ONLY).
 //
-// Mapping: ONE PAIR PER THREAD.  A 2-word window offers only a 2-way wavefront, so throughput comes from pairs in
-// flight.  Per thread, shared memory holds only what the walk can read: the bottom-right 64x64 quadrant of the
-// window (65 columns of one funnel-shifted 64-row slice of Pv and Mv — the reference keeps all 130 columns x 2 words,
-// bpm_windowed.c:143) plus the 10 window-aligned match masks.  Layout [slot][thread] makes every access
-// conflict-free regardless of the per-thread slot (blockDim.x is a multiple of 16).
+// Mapping: ONE PAIR PER THREAD, persistent grid.  A 2-word window offers only a 2-way wavefront, so throughput comes
+// from pairs in flight.  Only what the walk can read is kept: the bottom-right 64x64 quadrant of the window (65
+// columns of one funnel-shifted 64-row slice of Pv and Mv — the reference keeps all 130 columns x 2 words,
+// bpm_windowed.c:143).  The 10 window-aligned match masks live in shared memory ([slot][thread], conflict-free).
 //
 // SSE=true reproduces the observable behaviour of windowed_compute_window_sse (bpm_windowed.c:283-445), which is
 // what the reference runs on x86 unless force_scalar is set (dispatch :577); SSE=false follows the scalar
@@ -18,103 +17,138 @@
 
 namespace qb {
 
-constexpr int kWsSlots = 65 * 2 + 2 * kAlpha;   // u64 slots of shared memory per thread
+constexpr int kWsThreads = 128;                 // threads per CTA of the WindowEd(S) kernel
+constexpr int kWsCtasPerSm = 6;                 // 768 resident threads per SM (register budget 85 per thread)
+constexpr int kWsQuadSlots = 65 * 2;            // u64 slots per thread in the quadrant scratch ([slot][thread] layout)
 
 template <bool SSE>
-__global__ void __launch_bounds__(64, 3)
+__global__ void __launch_bounds__(kWsThreads, kWsCtasPerSm)
 k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigned char *__restrict__ codes,
                    const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, int hew_threshold,
-                   int *__restrict__ bound, int *__restrict__ hew_out, u64 *__restrict__ counters)
+                   int *__restrict__ bound, int *__restrict__ hew_out, u64 *__restrict__ counters,
+                   u64 *__restrict__ quad)
 {
-    extern __shared__ u64 sm[];
-    const int T = blockDim.x, t = threadIdx.x;
-    u64 *qpv = sm + t;                    // [65][T]  Pv slice of stored column idx cs+s
-    u64 *qmv = sm + 65 * T + t;           // [65][T]
-    u64 *weq = sm + 130 * T + t;          // [2*5][T] window-aligned match masks
-    const int i = blockIdx.x * T + t;
+    __shared__ u64 s_weq[2 * kAlpha * kWsThreads];          // [2*5][T] window-aligned match masks
+    const int T = kWsThreads, t = threadIdx.x;
+    u64 *weq = s_weq + t;
+    const i64 gtid = (i64)blockIdx.x * T + t, nthr = (i64)gridDim.x * T;
+    // Quadrant scratch: [slot][resident thread] in HBM/L2 (reused window after window, pair after pair, so it stays
+    // L2-resident); a shared-memory copy would cap the SM at ~200 threads and leave it latency-bound.
+    u64 *qpv = quad + gtid;                                  // slot s at qpv[s * nthr]
+    u64 *qmv = quad + 65 * nthr + gtid;
+    const int hew_lim = 64 * hew_threshold / 100;            // (W-O)*64*thr/100, bpm_windowed.c:555
     u64 ws = 0;
-    if (i < n_pairs) {
+    for (i64 i = gtid; i < n_pairs; i += nthr) {
         const PairRec pr = pairs[i];
-        const unsigned char *tc = codes + pr.t_off;
-        const unsigned char *traw = raw + pr.t_off, *praw = raw + pr.p_off;
-        const u64 *pq = peq + pr.peq_off;
-        const int nbp = pr.nbp;
-        const int hew_lim = 64 * hew_threshold / 100;          // (W-O)*64*thr/100, bpm_windowed.c:555
-        int cv = pr.m - 1, ch = pr.n - 1, score = 0, hew = 0;  // corner (pos_v,pos_h), bpm_windowed.c:148-149
-        while (cv >= 0 && ch >= 0) {
-            // ---- window geometry (bpm_windowed.c:219-232) ----
-            const int v0 = max(cv - 127, 0), h0 = max(ch - 127, 0);
-            const int words = ((cv - v0) >> 6) + 1, cols = ch - h0 + 1;
-            const int v_stop = max(cv - 63, 0), h_stop = max(ch - 63, 0);
-            const int cs = h_stop - h0;                 // first stored column index the walk can touch
-            const unsigned r0 = (unsigned)(v_stop - v0); // first row of the 64-row slice, 0..64
-            // ---- match masks re-aligned to the window origin (bpm_windowed.c:237-244) ----
-            {
-                const unsigned sh = v0 & 63;
-                const int blk0 = v0 >> 6;
+        int score = 0, hew = 0;
+        int cv = pr.m - 1, ch = pr.n - 1;                    // corner (pos_v,pos_h), bpm_windowed.c:148-149
+        if (pr.m > 0 && pr.n > 0) {
+            const unsigned char *tc = codes + pr.t_off;
+            const unsigned char *traw = raw + pr.t_off, *praw = raw + pr.p_off;
+            const u64 *pq = peq + pr.peq_off;
+            const int nbp = pr.nbp;
+            while (cv >= 0 && ch >= 0) {
+                // ---- window geometry (bpm_windowed.c:219-232) ----
+                const int v0 = max(cv - 127, 0), h0 = max(ch - 127, 0);
+                const int words = ((cv - v0) >> 6) + 1, cols = ch - h0 + 1;
+                const int v_stop = max(cv - 63, 0), h_stop = max(ch - 63, 0);
+                const int cs = h_stop - h0;                  // first stored column index the walk can touch
+                const unsigned r0 = (unsigned)(v_stop - v0); // first row of the 64-row slice, 0..64
+                // ---- match masks re-aligned to the window origin (bpm_windowed.c:237-244) ----
+                {
+                    const unsigned sh = v0 & 63;
+                    const int blk0 = v0 >> 6;
+                    u64 a[kAlpha], b[kAlpha], c2[kAlpha];
 #pragma unroll
-                for (int c = 0; c < kAlpha; ++c) {
-                    const u64 a = pq[(i64)c * nbp + blk0], b = pq[(i64)c * nbp + blk0 + 1];
-                    weq[c * T] = funnel_r(a, b, sh);
-                    u64 e1 = 0;
-                    if (words == 2) e1 = funnel_r(b, pq[(i64)c * nbp + blk0 + 2], sh);
-                    weq[(kAlpha + c) * T] = e1;
+                    for (int c = 0; c < kAlpha; ++c) {
+                        a[c] = pq[(i64)c * nbp + blk0]; b[c] = pq[(i64)c * nbp + blk0 + 1];
+                        c2[c] = (words == 2) ? pq[(i64)c * nbp + blk0 + 2] : 0ull;
+                    }
+#pragma unroll
+                    for (int c = 0; c < kAlpha; ++c) {
+                        weq[c * T] = funnel_r(a[c], b[c], sh);
+                        weq[(kAlpha + c) * T] = (words == 2) ? funnel_r(b[c], c2[c], sh) : 0ull;
+                    }
                 }
-            }
-            u64 pv0 = (h0 == 0) ? ~0ull : 0ull, pv1 = pv0, mv0 = 0, mv1 = 0;   // :225-229
-            const u32 top_in = (v0 == 0);                                      // :247-252
-            u64 pv1_prev = 0, mv1_prev = 0;
-            if (cs == 0) {
-                qpv[0] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
-                qmv[0] = 0;
-            }
-            for (int c = 0; c < cols; ++c) {
-                const int code = tc[h0 + c];
-                u32 hp_in0 = top_in;
-                if (SSE && c > 0) hp_in0 = (c == 1) | ((c & 1) ^ 1);           // :348,:393,:424
-                u32 hp, hm, o1, o2;
-                myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
-                if (words == 2) {
-                    if (SSE && c == cols - 1) { pv1_prev = pv1; mv1_prev = mv1; }
-                    if (SSE && cols == 1) { hp = 0; hm = 0; }                  // uninitialised carry in the reference
-                    myers_step(weq[(kAlpha + code) * T], pv1, mv1, hp, hm, o1, o2);
+                u64 pv0 = (h0 == 0) ? ~0ull : 0ull, pv1 = pv0, mv0 = 0, mv1 = 0;   // :225-229
+                const u32 top_in = (v0 == 0);                                      // :247-252
+                u64 pv1_prev = 0, mv1_prev = 0;
+                if (cs == 0) {
+                    qpv[0] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
+                    qmv[0] = 0;
                 }
-                if (c + 1 >= cs) {
-                    const int s = c + 1 - cs;
-                    qpv[s * T] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
-                    qmv[s * T] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
+                for (int c0 = 0; c0 < cols; c0 += 8) {
+                    // eight independent byte loads in flight instead of one dependent load per column
+                    u32 cd[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) cd[k] = (c0 + k < cols) ? (u32)tc[h0 + c0 + k] : 4u;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int c = c0 + k;
+                        if (c < cols) {
+                            const int code = (int)cd[k];
+                            u32 hp_in0 = top_in;
+                            if (SSE && c > 0) hp_in0 = (c == 1) | ((c & 1) ^ 1);       // :348,:393,:424
+                            u32 hp, hm, o1, o2;
+                            myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
+                            if (words == 2) {
+                                if (SSE && c == cols - 1) { pv1_prev = pv1; mv1_prev = mv1; }
+                                if (SSE && cols == 1) { hp = 0; hm = 0; }              // uninitialised carry in the reference
+                                myers_step(weq[(kAlpha + code) * T], pv1, mv1, hp, hm, o1, o2);
+                            }
+                            if (c + 1 >= cs) {
+                                const i64 s = (i64)(c + 1 - cs) * nthr;
+                                qpv[s] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
+                                qmv[s] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
+                            }
+                        }
+                    }
                 }
+                ws += (u64)(words * cols);
+                if (SSE && words == 2 && !(cols & 1)) {
+                    // look-ahead column of word 0 (:361) and the redone last column of word 1 (:428-444)
+                    const int ti = h0 + cols;
+                    const int code_la = (ti < pr.n) ? (int)tc[ti] : 4;
+                    u64 lpv = pv0, lmv = mv0;
+                    u32 hpL, hmL, o1, o2;
+                    myers_step(weq[code_la * T], lpv, lmv, 1u, 0u, hpL, hmL);
+                    const int code_last = tc[h0 + cols - 1];
+                    pv1 = pv1_prev; mv1 = mv1_prev;
+                    myers_step(weq[(kAlpha + code_last) * T], pv1, mv1, hpL, hmL, o1, o2);
+                    const i64 s = (i64)(cols - cs) * nthr;
+                    qpv[s] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
+                    qmv[s] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
+                }
+                // ---- walk back through the non-overlapping 64 rows/columns (bpm_windowed.c:504-561): D, I, M, X ----
+                // The next column's words are prefetched one column ahead, and the raw-byte compare of a diagonal
+                // step (it only decides the cost, never the path) is consumed one step later.
+                int v = cv, h = ch, cost = 0;
+                int jp = h - h_stop + 1;                     // stored column index of Pv for the current h
+                u64 dp = qpv[(i64)jp * nthr], im = qmv[(i64)(jp - 1) * nthr];
+                u64 dpn = 0, imn = 0;
+                if (jp >= 2) { dpn = qpv[(i64)(jp - 1) * nthr]; imn = qmv[(i64)(jp - 2) * nthr]; }
+                u32 pend_t = 0, pend_p = 0;
+                while (v >= v_stop && jp >= 1) {
+                    const int bit = v - v_stop;
+                    cost += (pend_t != pend_p);
+                    pend_t = pend_p = 0;
+                    if ((dp >> bit) & 1ull) { ++cost; --v; }
+                    else {
+                        if ((im >> bit) & 1ull) ++cost;
+                        else { pend_t = traw[h]; pend_p = praw[v]; --v; }
+                        --h; --jp;
+                        dp = dpn; im = imn;
+                        if (jp >= 2) { dpn = qpv[(i64)(jp - 1) * nthr]; imn = qmv[(i64)(jp - 2) * nthr]; }
+                    }
+                }
+                cost += (pend_t != pend_p);
+                if (cost > hew_lim) ++hew;
+                score += cost;
+                cv = v; ch = h;
             }
-            ws += (u64)(words * cols);
-            if (SSE && words == 2 && !(cols & 1)) {
-                // look-ahead column of word 0 (:361) and the redone last column of word 1 (:428-444)
-                const int ti = h0 + cols;
-                const int code_la = (ti < pr.n) ? (int)tc[ti] : 4;
-                u64 lpv = pv0, lmv = mv0;
-                u32 hpL, hmL, o1, o2;
-                myers_step(weq[code_la * T], lpv, lmv, 1u, 0u, hpL, hmL);
-                const int code_last = tc[h0 + cols - 1];
-                pv1 = pv1_prev; mv1 = mv1_prev;
-                myers_step(weq[(kAlpha + code_last) * T], pv1, mv1, hpL, hmL, o1, o2);
-                const int s = cols - cs;
-                qpv[s * T] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
-                qmv[s * T] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
-            }
-            // ---- walk back through the non-overlapping 64 rows/columns (bpm_windowed.c:504-561): D, I, M, X ----
-            int v = cv, h = ch, cost = 0;
-            while (v >= v_stop && h >= h_stop) {
-                const int bit = v - v_stop, jp = h - h_stop + 1;
-                const u64 dp = qpv[jp * T], im = qmv[(jp - 1) * T];
-                if ((dp >> bit) & 1ull) { ++cost; --v; }
-                else if ((im >> bit) & 1ull) { ++cost; --h; }
-                else { cost += (traw[h] != praw[v]); --h; --v; }
-            }
-            if (cost > hew_lim) ++hew;
-            score += cost;
-            cv = v; ch = h;
+            if (ch >= 0) score += ch + 1;      // bpm_windowed.c:599-607
+            if (cv >= 0) score += cv + 1;
         }
-        if (ch >= 0) score += ch + 1;      // bpm_windowed.c:599-607
-        if (cv >= 0) score += cv + 1;
         bound[i] = score;
         hew_out[i] = hew;
     }
@@ -123,7 +157,6 @@ k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigne
     for (int o = 16; o > 0; o >>= 1) ws += __shfl_down_sync(kFull, ws, o);
     if ((t & 31) == 0 && ws) atomicAdd(&counters[0], ws);
 }
-
 
 // ----------------------------------------------------------------------------------------------------------------
 // k_windowed_warp: WindowEd for ANY window / overlap (W <= 32 words), score-only or CIGAR mode, forward or

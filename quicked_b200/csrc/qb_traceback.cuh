@@ -53,7 +53,11 @@ __device__ __forceinline__ bool cell_written(const int2 *ranges, int B, int c, i
     return w >= lo && w <= r.y;
 }
 
-// One leaf per thread: simple pointer-chasing walk over the [column][band word] matrix written by k_banded_warp<.,true>.
+// One leaf per thread.  Works on both matrix layouts (warp kernel: [column][word]; thread kernel: 32 leaves
+// interleaved) through the task's column / word strides.  Per step the walk needs bit v of Pv[column h+1] and of
+// Mv[column h]; (Pv,Mv) of one (column, word) is a single 16-byte entry, so the entry fetched for Mv at column h
+// is reused for Pv when the walk moves to column h-1, and the live ranges are cached per 64-column block:
+// about one 16-byte load per visited column instead of four dependent loads per step.
 __global__ void __launch_bounds__(128)
 k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
                    const unsigned char *__restrict__ raw, const ulonglong2 *__restrict__ matrix,
@@ -68,22 +72,49 @@ k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ l
     const ulonglong2 *mat = matrix + tk.mat_off;
     const int2 *ranges = range_pool + tk.range_off;
     const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
+    const i64 cs = tk.mat_cs, wsd = tk.mat_ws;
     OpWriter w; w.init(ops_pool + tk.ops_off, tk.ops_cap);
     int h = tk.n - 1, v = tk.m - 1;
+    // cached live ranges of column blocks kb_c and kb_c + 1
+    int kb_c = -2; int2 rg0 = make_int2(0, -1), rg1 = make_int2(0, -1);
+    // cached entries: key = column * B + word (the reference's flat index), -1 = empty
+    i64 keyR = -1, keyL = -1;
+    ulonglong2 eR = make_ulonglong2(0, 0), eL = make_ulonglong2(0, 0);
+    auto fetch = [&](int c, int wd) -> ulonglong2 {
+        // never-written cells read as 0 (see cell_written); the live range of column c comes from block (c-1)/64
+        if (c < 0 || c > tk.n || wd < 0 || wd >= B) return make_ulonglong2(0, 0);
+        if (c > 0) {
+            const int kb = (c - 1) >> 6;
+            if (kb != kb_c) {
+                if (kb == kb_c + 1) rg0 = rg1; else rg0 = ranges[kb];
+                rg1 = ranges[kb + 1];
+                kb_c = kb;
+            }
+            const int lo = (c & 63) ? rg0.x : min(rg0.x, rg1.x);
+            if (wd < lo || wd > rg0.y) return make_ulonglong2(0, 0);
+        }
+        return mat[(i64)c * cs + (i64)wd * wsd];
+    };
     while (v >= 0 && h >= 0) {
         const int ev = v - 64 * ((h >> 6) - prolog);
         const int evr = v - 64 * (((h + 1) >> 6) - prolog);
-        // word numbers with C truncation (the reference divides a possibly negative row offset, bpm_banded.c:995-998)
-        int wr = evr / 64, wl = ev / 64, cr = h + 1, cl = h;
-        // a row outside the band's coordinates makes the reference index the flat [column][word] array across
-        // column boundaries; follow the same flat index (only possible when the band is too narrow)
-        if (wr < 0 || wr >= B) { const i64 f = (i64)cr * B + wr; cr = f >= 0 ? (int)(f / B) : -1; wr = f >= 0 ? (int)(f % B) : -1; }
-        if (wl < 0 || wl >= B) { const i64 f = (i64)cl * B + wl; cl = f >= 0 ? (int)(f / B) : -1; wl = f >= 0 ? (int)(f % B) : -1; }
-        u64 pvw = 0, mvw = 0;
-        if (cr >= 0 && cr <= tk.n && cell_written(ranges, B, cr, wr)) pvw = mat[(i64)cr * tk.mat_cs + (i64)wr * tk.mat_ws].x;
-        if (cl >= 0 && cl <= tk.n && cell_written(ranges, B, cl, wl)) mvw = mat[(i64)cl * tk.mat_cs + (i64)wl * tk.mat_ws].y;
-        if ((pvw >> (evr & 63)) & 1ull) { w.emit(OP_D); --v; }
-        else if ((mvw >> (ev & 63)) & 1ull) { w.emit(OP_I); --h; }
+        // word numbers with C truncation; a row outside the band's coordinates makes the reference index the flat
+        // [column][word] array across column boundaries (only possible when the band is too narrow)
+        const int wr = evr / 64, wl = ev / 64;
+        const i64 fR = (i64)(h + 1) * B + wr, fL = (i64)h * B + wl;
+        if (fR != keyR) {
+            if (fR == keyL) eR = eL;
+            else if (wr >= 0 && wr < B) eR = fetch(h + 1, wr);
+            else eR = fR >= 0 ? fetch((int)(fR / B), (int)(fR % B)) : make_ulonglong2(0, 0);
+            keyR = fR;
+        }
+        if (fL != keyL) {
+            if (wl >= 0 && wl < B) eL = fetch(h, wl);
+            else eL = fL >= 0 ? fetch((int)(fL / B), (int)(fL % B)) : make_ulonglong2(0, 0);
+            keyL = fL;
+        }
+        if ((eR.x >> (evr & 63)) & 1ull) { w.emit(OP_D); --v; }
+        else if ((eL.y >> (ev & 63)) & 1ull) { w.emit(OP_I); --h; }
         else { w.emit(traw[h] == praw[v] ? OP_M : OP_X); --h; --v; }
     }
     while (h >= 0) { w.emit(OP_I); --h; }

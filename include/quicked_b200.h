@@ -3,7 +3,7 @@
  *
  * The reference library aligns one pair per quicked_align() call; its only batching is the OpenMP loop in
  * the benchmark tool (reference: tools/align_benchmark/align_benchmark.c:232-306) over a packed
- * sequence buffer + offsets (reference: tools/align_benchmark/benchmark/sequence_buffer.h:30-50).  A GPU
+ * sequence buffer + offsets (reference: quicked_utils/include/sequence_buffer.h:30-50).  A GPU
  * needs the whole batch at once, so this header adds a batched entry point with that same packed layout.
  * quicked_align() (include/quicked.h) is a batch of one through the same code.
  *

@@ -59,7 +59,8 @@ struct LeafOut {
     int n_ops;            // ops emitted (they occupy the tail of the task's ops region)
     int cost;             // X+I+D count
     int text_len;         // bytes of the RLE text of this leaf alone (without NUL)
-    int first_op, first_run;   // leftmost op code and its run length (for cross-leaf merging)
+    int fmt;              // 0: ops are 2-bit codes, 16 per u32 (thread walk); 1: u32 runs (len<<2 | op) (warp walk)
+    int pad_;
 };
 
 // ---- BandEd geometry: reference bpm_banded.c:121-135 (allocate), :359-361/:801-803 (score-only height) ----

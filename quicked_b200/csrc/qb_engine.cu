@@ -274,9 +274,17 @@ int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks
     return 0;
 }
 
-int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub)
+int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub, bool warp_layout = false)
 {
     if (n_tasks <= 0) return 0;
+    if (warp_layout) {      // leaves written by the warp kernel: cooperative, tile-prefetching walk
+        k_traceback_warp<<<(n_tasks + kTraceWarpsPerCta - 1) / kTraceWarpsPerCta, 32 * kTraceWarpsPerCta, 0, ctx->stream>>>(
+            ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub, ctx->raw(), ctx->d_matrix.as<ulonglong2>(),
+            ctx->d_ranges.as<int2>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>());
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        return 0;
+    }
     k_traceback_thread<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub,
                                                                         ctx->raw(), ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(),
                                                                         ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>());
@@ -601,7 +609,8 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
             }
             {
                 Span sp(ctx, ST_TRACE);
-                int rc = launch_traceback(ctx, nullptr, 0, (int)tot.leaf, 0);
+                int rc = launch_traceback(ctx, ctx->d_list_t.as<int>(), 0, (int)tot.t, 0, false);
+                if (!rc) rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, true);
                 if (rc) return rc;
             }
             ctx->stats.matrix_bytes += need * 16;
@@ -617,7 +626,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
                 const int s1 = *reinterpret_cast<int *>(ctx->h_pinned);
                 const i64 sub = *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
                 { Span sp(ctx, ST_FILL); int rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
-                { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
+                { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub, true); if (rc) return rc; }
                 s0 = s1;
             }
             // thread-kernel groups
@@ -851,7 +860,7 @@ int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
         }
         {
             Span sp(ctx, ST_TRACE);
-            int rc = launch_traceback(ctx, lst, c.q0, c.q1 - c.q0, 0);
+            int rc = launch_traceback(ctx, lst, c.q0, c.q1 - c.q0, 0, !c.thr);
             if (rc) return rc;
         }
         ctx->stats.matrix_bytes += c.ent * 16;
@@ -1133,7 +1142,8 @@ static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std:
             BandTask lf{};
             lf.p_off = nd.p_off; lf.t_off = nd.t_off; lf.m = nd.m; lf.n = nd.n; lf.rev = 0; lf.finish = nd.n; lf.cutoff = nd.cutoff;
             lf.nbp = (nd.m + 63) / 64 + 2; lf.pair = slow_pairs[q];
-            lf.ops_cap = ((nd.m + nd.n + 15) / 16) * 16; lf.ops_off = ops_words; ops_words += lf.ops_cap / 16;
+            lf.ops_cap = ((nd.m + nd.n + 15) / 16) * 16; lf.ops_off = ops_words;
+            ops_words += (band_geometry(nd.m, nd.n, nd.cutoff).Bc <= kThreadBandMax) ? lf.ops_cap / 16 : lf.ops_cap;   // u32 runs for warp walks
             lf.slot = (int)(L0 + (i64)leaves.size());
             if (res[q].pl.n_leaves == 0) res[q].pl.first_leaf = lf.slot;
             res[q].pl.n_leaves++;

@@ -81,7 +81,7 @@ k_plan(const PairRec *__restrict__ pairs, int n, PlanParams pp, const int *__res
                 c = thr ? CLS_T : CLS_W;
                 st = pp.ok_status;
                 it.leaf = 1; it.t = thr; it.w = !thr;
-                it.ops = (r.m + r.n + 15) / 16;
+                it.ops = thr ? (r.m + r.n + 15) / 16 : (r.m + r.n + 15) / 16 * 16;  // 2-bit ops (thread walk) / u32 runs, worst case (warp walk)
                 it.rng = r.n / 64 + 2;
                 if (!thr) { it.sc = (r.m + 63) / 64 + g.Bc + 2; it.matw = (i64)(r.n + 1) * g.Bc; }
             }

@@ -122,8 +122,143 @@ k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ l
     w.finish();
     LeafOut o;
     o.n_ops = tk.ops_cap - w.pos; o.cost = w.cost; o.text_len = w.text_len;
-    o.first_op = w.cur_op; o.first_run = w.cur_len;
+    o.fmt = 0; o.pad_ = 0;
     outs[tk.slot] = o;
+}
+
+// One leaf per WARP, for leaves written by the warp kernel ([column][band word] layout, long pairs).
+// The reference's walk is a 1-bit-per-step dependent chain (bpm_banded.c:987-1023).  Here it is word-parallel:
+//   * the 32 lanes prefetch, in ONE HBM round trip, a tile of the traceback state around the current cell
+//     (32 columns x the 2 blocks covering rows v-64..v) into shared memory;
+//   * lane l then PROBES the cell l steps down the diagonal, (v-l, h-l): its D bit, its I bit and its raw-byte
+//     compare.  One ballot finds the first cell that is not a plain diagonal move; all the M/X ops before it are
+//     emitted at once (one coalesced byte store), then the single D or I of that cell, and the probe restarts there.
+// With ~17 % error a probe advances ~6 steps for the instruction cost of ~1.5 serial steps.  The tile is only a
+// cache in front of the same fetch rules as k_traceback_thread (live ranges, flat-index quirks of too-narrow
+// bands are walked one serial step at a time), so results are identical.  The output is already run-length
+// encoded: u32 runs (len<<2 | op) written right to left (LeafOut.fmt = 1), with the exact text length.
+constexpr int kTraceWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(32 * kTraceWarpsPerCta)
+k_traceback_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
+                 const unsigned char *__restrict__ raw, const ulonglong2 *__restrict__ matrix,
+                 const int2 *__restrict__ range_pool, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
+{
+    __shared__ ulonglong2 s_tile[kTraceWarpsPerCta][32][2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int id = blockIdx.x * kTraceWarpsPerCta + wib;
+    if (id >= n_tasks) return;
+    BandTask tk = tasks[list ? list[begin + id] : begin + id];
+    tk.mat_off -= mat_sub;
+    const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+    const int B = (int)g.Bc, prolog = (int)g.prolog;
+    const ulonglong2 *mat = matrix + tk.mat_off;
+    const int2 *ranges = range_pool + tk.range_off;
+    const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
+    const i64 cs = tk.mat_cs, wsd = tk.mat_ws;
+    ulonglong2 (*tile)[2] = s_tile[wib];
+    u32 *runs = ops_pool + tk.ops_off;       // u32 runs (len<<2 | op), written right to left; capacity ops_cap words
+    int rpos = tk.ops_cap;                   // next run goes to rpos-1
+    int cur_op = -1, cur_len = 0, text_len = 0;      // open run (warp-uniform)
+    auto emit_run = [&](int op, int len) {
+        if (op == cur_op) { cur_len += len; return; }
+        if (cur_len) { if (lane == 0) runs[rpos - 1] = ((u32)cur_len << 2) | (u32)cur_op; --rpos; text_len += dec_digits((unsigned)cur_len) + 1; }
+        cur_op = op; cur_len = len;
+    };
+    auto fetch = [&](int c, int wd) -> ulonglong2 {          // same rules as k_traceback_thread::fetch
+        if (c < 0 || c > tk.n || wd < 0 || wd >= B) return make_ulonglong2(0, 0);
+        if (c > 0) {
+            const int kb = (c - 1) >> 6;
+            const int2 r0 = ranges[kb];
+            const int lo = (c & 63) ? r0.x : min(r0.x, ranges[kb + 1].x);
+            if (wd < lo || wd > r0.y) return make_ulonglong2(0, 0);
+        }
+        return mat[(i64)c * cs + (i64)wd * wsd];
+    };
+    int h = tk.n - 1, v = tk.m - 1;          // warp-uniform
+    int cost = 0;
+    while (v >= 0 && h >= 0) {
+        // ---- (re)load the tile: columns c_hi-31..c_hi, absolute blocks bA-1, bA ----
+        const int c_hi = h + 1, bA = v >> 6;
+        {
+            const int c = c_hi - lane;
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) {
+                const int b = bA - 1 + sidx;
+                ulonglong2 e = make_ulonglong2(0, 0);
+                if (c >= 0 && b >= 0) e = fetch(c, b - ((c >> 6) - prolog));
+                tile[lane][sidx] = e;
+            }
+        }
+        __syncwarp();
+        // ---- probe along the diagonal until the walk leaves the tile ----
+        while (v >= 0 && h >= 0) {
+            const int vl = v - lane, hl = h - lane;
+            bool inside = vl >= 0 && hl >= 0;
+            const int ev = vl - 64 * ((hl >> 6) - prolog);
+            const int evr = vl - 64 * (((hl + 1) >> 6) - prolog);
+            const int wr = evr >> 6, wl = ev >> 6;
+            const int tl = c_hi - hl, br = (vl >> 6) - (bA - 1);
+            const bool regular = ev >= 0 && evr >= 0 && wr < B && wl < B;
+            const bool in_tile = tl <= 31 && br >= 0;
+            bool isD = false, isI = false, mm = false;
+            if (inside && regular && in_tile) {
+                const ulonglong2 eR = tile[tl - 1][br], eL = tile[tl][br];
+                isD = (eR.x >> (evr & 63)) & 1ull;
+                isI = (eL.y >> (ev & 63)) & 1ull;
+                mm = traw[hl] != praw[vl];
+            }
+            const u32 stop = __ballot_sync(kFull, !inside || !regular || !in_tile || isD || isI);
+            const u32 mmask = __ballot_sync(kFull, mm);
+            const int nd = stop ? (__ffs(stop) - 1) : 32;        // leading plain-diagonal cells
+            {   // the nd diagonal ops, lane 0's first: split the mismatch mask into runs of equal bits
+                u32 bits = mmask & (nd >= 32 ? kFull : ((1u << nd) - 1u));
+                cost += __popc(bits);
+                int left = nd;
+                while (left > 0) {
+                    const int x = bits & 1u;
+                    const u32 t = x ? ~bits : bits;                  // run of the low bit's value
+                    int len = t ? (__ffs(t) - 1) : 32;
+                    len = min(len, left);
+                    emit_run(x ? OP_X : OP_M, len);
+                    bits = (len >= 32) ? 0u : (bits >> len);
+                    left -= len;
+                }
+            }
+            v -= nd; h -= nd;
+            if (nd == 32) continue;
+            // lane nd holds the first non-diagonal cell: broadcast why it stopped
+            const u32 why = __shfl_sync(kFull, (u32)(isD ? 1u : isI ? 2u : (!inside ? 4u : (!in_tile ? 8u : 16u))), nd);
+            if (why == 1u) { emit_run(OP_D, 1); ++cost; --v; }
+            else if (why == 2u) { emit_run(OP_I, 1); ++cost; --h; }
+            else if (why == 4u) break;                           // ran off the matrix: leftovers below
+            else if (why == 8u) break;                           // left the tile: reload it
+            else {
+                // too-narrow band: this cell follows the reference's flat-index quirks; one serial step (all lanes
+                // compute the same thing, lane 0 writes)
+                const int e0 = v - 64 * ((h >> 6) - prolog), e1 = v - 64 * (((h + 1) >> 6) - prolog);
+                const int w1 = e1 / 64, w0 = e0 / 64;
+                const i64 fR = (i64)(h + 1) * B + w1, fL = (i64)h * B + w0;
+                const ulonglong2 eR = (w1 >= 0 && w1 < B) ? fetch(h + 1, w1) : (fR >= 0 ? fetch((int)(fR / B), (int)(fR % B)) : make_ulonglong2(0, 0));
+                const ulonglong2 eL = (w0 >= 0 && w0 < B) ? fetch(h, w0) : (fL >= 0 ? fetch((int)(fL / B), (int)(fL % B)) : make_ulonglong2(0, 0));
+                int op;
+                if ((eR.x >> (e1 & 63)) & 1ull) { op = OP_D; --v; }
+                else if ((eL.y >> (e0 & 63)) & 1ull) { op = OP_I; --h; }
+                else { op = traw[h] == praw[v] ? OP_M : OP_X; --h; --v; }
+                emit_run(op, 1); cost += (op != OP_M);
+            }
+        }
+        __syncwarp();
+    }
+    // leftovers: I... then D... (bpm_banded.c:1025-1034)
+    if (h >= 0) { emit_run(OP_I, h + 1); cost += h + 1; }
+    if (v >= 0) { emit_run(OP_D, v + 1); cost += v + 1; }
+    emit_run(-1, 0);                                                       // flush the open run
+    if (lane == 0) {
+        LeafOut o;
+        o.n_ops = tk.ops_cap - rpos; o.cost = cost; o.text_len = text_len; o.fmt = 1; o.pad_ = 0;
+        outs[tk.slot] = o;
+    }
 }
 
 // Per-pair list of leaves (left to right).  Single-leaf pairs: n_leaves == 1.
@@ -159,10 +294,23 @@ k_cigar_text(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask *__r
     int out = 0, cur_op = -1, cur_len = 0;
     for (int l = 0; l < p.n_leaves; ++l) {
         const BandTask tk = leaves[p.first_leaf + l];
-        const int n_ops = leaf_out[p.first_leaf + l].n_ops;
+        const LeafOut lo = leaf_out[p.first_leaf + l];
+        const int n_ops = lo.n_ops;
         const u32 *words = ops_pool + tk.ops_off;
         int pos = tk.ops_cap - n_ops;
         const int end = tk.ops_cap;
+        if (lo.fmt == 1) {                           // u32 runs (warp traceback)
+            for (; pos < end; ++pos) {
+                const u32 r = words[pos];
+                const int op = (int)(r & 3u), len = (int)(r >> 2);
+                if (op == cur_op) cur_len += len;
+                else {
+                    if (cur_len) out += WRITE ? put_run(dst + out, cur_len, cur_op) : dec_digits((unsigned)cur_len) + 1;
+                    cur_op = op; cur_len = len;
+                }
+            }
+            continue;
+        }
         while (pos < end) {
             const u32 wv = words[pos >> 4];
             const int stop = min(end, (pos | 15) + 1);

@@ -296,7 +296,7 @@ k_windowed_warp(const WinTask *__restrict__ tasks, int n_tasks, const unsigned c
             for (int v = cv; v >= 0; --v) ow.emit(OP_D);
             ow.finish();
             LeafOut o;
-            o.n_ops = tk.ops_cap - ow.pos; o.cost = ow.cost; o.text_len = ow.text_len; o.first_op = ow.cur_op; o.first_run = ow.cur_len;
+            o.n_ops = tk.ops_cap - ow.pos; o.cost = ow.cost; o.text_len = ow.text_len; o.fmt = 0; o.pad_ = 0;
             leaf_outs[tk.leaf_slot] = o;
             score = ow.cost;
         }

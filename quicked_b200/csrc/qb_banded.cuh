@@ -350,7 +350,7 @@ k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ li
 // The lane's 5 match masks per live block are staged in shared memory ([slot][thread], conflict-free) once per
 // 64 columns; the per-column fetch is an LDS indexed by the column's code.
 template <int BMAX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
                 const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
                 int2 *__restrict__ range_pool, u64 *__restrict__ counters)
@@ -365,7 +365,7 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
         tk.mat_off -= mat_sub;
         const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
         const int B = (int)g.Bc, prolog = (int)g.prolog;
-        const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63, clamp = nblk - 1;
+        const int nblk = (tk.m + 63) >> 6, clamp = nblk - 1;
         const i64 fin = g.fin, kcut = g.k;
         const u64 *pq = peq + tk.peq_off;
         const unsigned char *tcodes = codes + tk.t_off;
@@ -383,29 +383,41 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
         ranges[0] = make_int2(first, last);
         for (int col0 = 0; col0 < tk.n; col0 += 64) {
             const int nc = min(64, tk.n - col0);
-            int ob[BMAX];
 #pragma unroll
             for (int j = 0; j < BMAX; ++j) {
                 const int blk = j + pos_v;
-                ob[j] = (blk == nblk - 1 && mmod) ? mmod - 1 : 63;
                 if (j >= first && j <= last) {
 #pragma unroll
                     for (int c = 0; c < kAlpha; ++c)
                         s_eq[(j * kAlpha + c) * T] = (blk < tk.nbp) ? pq[(i64)c * tk.nbp + blk] : 0ull;
                 }
             }
-            for (int c = 0; c < nc; ++c) {
-                const int code = tk.rev ? tcodes[tk.n - 1 - (col0 + c)] : tcodes[col0 + c];
-                ulonglong2 *dst = mat + (i64)(col0 + c + 1) * cs;
-                u32 hp = 1, hm = 0;
+            // In full-matrix mode the level mask of the last pattern block (bpm_banded.c:88-102) can be ignored: it only
+            // changes the carry into rows >= m (never visited by the traceback) and the running score of blocks that
+            // the cut tests never look at (the bottom clamp keeps them out), so every block uses the bit-63 carry.
+            for (int c0 = 0; c0 < nc; c0 += 8) {
+                u32 cd[8];                                  // eight independent code loads in flight
 #pragma unroll
-                for (int j = 0; j < BMAX; ++j) {
-                    if (j >= first && j <= last) {
-                        u32 hpo, hmo;
-                        myers_step_at(s_eq[(j * kAlpha + code) * T], pv[j], mv[j], hp, hm, ob[j], hpo, hmo);
-                        sc[j] += (int)hpo - (int)hmo;
-                        hp = hpo; hm = hmo;
-                        dst[j * wsd] = make_ulonglong2(pv[j], mv[j]);
+                for (int k = 0; k < 8; ++k) {
+                    const int col = col0 + c0 + k;
+                    cd[k] = (c0 + k < nc) ? (u32)(tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col]) : 4u;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (c0 + k < nc) {
+                        const int code = (int)cd[k];
+                        ulonglong2 *dst = mat + (i64)(col0 + c0 + k + 1) * cs;
+                        u32 hp = 1, hm = 0;
+#pragma unroll
+                        for (int j = 0; j < BMAX; ++j) {
+                            if (j >= first && j <= last) {
+                                u32 hpo, hmo;
+                                myers_step(s_eq[(j * kAlpha + code) * T], pv[j], mv[j], hp, hm, hpo, hmo);
+                                sc[j] += (int)hpo - (int)hmo;
+                                hp = hpo; hm = hmo;
+                                dst[j * wsd] = make_ulonglong2(pv[j], mv[j]);
+                            }
+                        }
                     }
                 }
             }

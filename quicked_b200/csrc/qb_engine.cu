@@ -9,7 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -92,6 +95,8 @@ struct qb200_ctx {
     DevBuf d_quad;                         // WindowEd(S) quadrant scratch
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
+    static constexpr int kWorkers = 8;
+    qb200_ctx *child[kWorkers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // workers of the pipelined qb200_align_batch
     std::vector<int> h_score, h_status;
     std::vector<i64> h_cigoff_;
     i64 cigar_total = 0;
@@ -352,6 +357,7 @@ int qb200_create(qb200_ctx_t **out, int device)
 void qb200_destroy(qb200_ctx_t *ctx)
 {
     if (!ctx) return;
+    for (int k = 0; k < qb200_ctx::kWorkers; ++k) if (ctx->child[k]) { qb200_destroy(ctx->child[k]); ctx->child[k] = nullptr; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->d_raw, &ctx->d_codes, &ctx->d_pairs, &ctx->d_peq, &ctx->d_peqjobs, &ctx->d_bound, &ctx->d_hew,
@@ -1247,8 +1253,132 @@ int qb200_measure_int_peak(qb200_ctx_t *ctx, double *tera_ops_per_s)
     return 0;
 }
 
+// Pipelined host-in / host-out path: the batch is cut into sub-batches of about one resident wave of the WindowEd
+// kernel; four worker contexts (own stream, own pools, own host thread) take sub-batches round-robin, so the H2D copy
+// of one overlaps the kernels and the D2H copies of the others and the PCIe link stays busy.  CIGAR strings stay packed in input order: a worker waits for the text
+// totals of the preceding sub-batches (known right after their run) before it downloads into the caller's buffer.
+static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res)
+{
+    const i64 n = b->n_pairs;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const i64 sub = (i64)sms * kWsCtasPerSm * kWsThreads;
+    const int S = (int)((n + sub - 1) / sub);
+    int NW = 3;
+    if (const char *e = getenv("QB200_WORKERS")) NW = std::max(1, std::min(atoi(e), (int)qb200_ctx::kWorkers));
+    const bool trace = getenv("QB200_TRACE") != nullptr;
+    for (int k = 0; k < NW; ++k) {
+        if (!ctx->child[k]) {
+            int rc = qb200_create(&ctx->child[k], ctx->device);
+            if (rc) return rc;
+        }
+        ctx->child[k]->matrix_limit = ctx->matrix_limit / NW;
+    }
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<i64> text_total((size_t)S, -1);        // bytes of CIGAR text of each sub-batch, -1 = not known yet
+    std::vector<int> rcs(NW, 0);
+    std::vector<qb200_stats_t> acc(NW);
+    memset(acc.data(), 0, sizeof(qb200_stats_t) * NW);
+    const bool want_cigar = !params->only_score && res->cigar_off;
+    bool capacity_short = false;
+
+    auto worker = [&](int wid) {
+        qb200_ctx *c = ctx->child[wid];
+        cudaSetDevice(c->device);
+        for (int sidx = wid; sidx < S; sidx += NW) {
+            const i64 i0 = (i64)sidx * sub, i1 = std::min(n, i0 + sub), cnt = i1 - i0;
+            int rc = 0;
+            // byte range of this sub-batch in the caller's packed buffer
+            i64 lo = b->seqs_bytes, hi = 0;
+            for (i64 i = i0; i < i1; ++i) {
+                lo = std::min<i64>(lo, std::min<i64>(b->pattern_off[i], b->text_off[i]));
+                hi = std::max<i64>(hi, std::max<i64>(b->pattern_off[i] + b->pattern_len[i], b->text_off[i] + b->text_len[i]));
+            }
+            if (hi < lo) { lo = 0; hi = 0; }
+            std::vector<int64_t> po((size_t)cnt), to((size_t)cnt);
+            for (i64 i = 0; i < cnt; ++i) { po[(size_t)i] = b->pattern_off[i0 + i] - lo; to[(size_t)i] = b->text_off[i0 + i] - lo; }
+            qb200_batch_t sb = {b->seqs + lo, hi - lo, cnt, po.data(), b->pattern_len + i0, to.data(), b->text_len + i0};
+            const auto t_a = std::chrono::steady_clock::now();
+            rc = qb200_upload(c, &sb);
+            const auto t_b = std::chrono::steady_clock::now();
+            if (!rc) rc = qb200_run(c, params);
+            const auto t_c = std::chrono::steady_clock::now();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                text_total[(size_t)sidx] = rc ? 0 : (want_cigar && c->have_cigar ? c->cigar_total : 0);
+                if (rc && !rcs[wid]) { rcs[wid] = rc; ctx->err = c->err; }
+            }
+            cv.notify_all();
+            if (rc) continue;
+            // where do this sub-batch's strings start?  wait for the totals of all earlier sub-batches
+            i64 base = 0;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { for (int q = 0; q < sidx; ++q) if (text_total[(size_t)q] < 0) return false; return true; });
+                for (int q = 0; q < sidx; ++q) base += text_total[(size_t)q];
+            }
+            std::vector<int64_t> loc_off;
+            if (res->cigar_off) loc_off.resize((size_t)cnt + 1);
+            qb200_results_t sr;
+            sr.score = res->score ? res->score + i0 : nullptr;
+            sr.status = res->status ? res->status + i0 : nullptr;
+            sr.cigar_off = res->cigar_off ? loc_off.data() : nullptr;
+            const i64 need = text_total[(size_t)sidx];
+            const bool fits = want_cigar && res->cigar && base + need <= res->cigar_capacity;
+            sr.cigar = fits ? res->cigar + base : nullptr;
+            sr.cigar_capacity = fits ? res->cigar_capacity - base : 0;
+            sr.cigar_bytes = 0;
+            rc = qb200_download(c, &sr);
+            if (rc == QB200_ERR_CAPACITY) { std::lock_guard<std::mutex> lk(mu); capacity_short = true; rc = 0; }
+            if (trace) {
+                const auto t_d = std::chrono::steady_clock::now();
+                auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
+                fprintf(stderr, "[qb200 pipeline] worker %d sub %d: upload %.2f ms, run %.2f ms (gpu %.2f), download %.2f ms\n", wid, sidx, ms(t_a, t_b), ms(t_b, t_c), c->stats.ms_total, ms(t_c, t_d));
+            }
+            if (res->cigar_off) for (i64 i = 0; i < cnt; ++i) res->cigar_off[i0 + i] = (want_cigar ? loc_off[(size_t)i] + base : 0);   // local -> global
+            if (rc && !rcs[wid]) { std::lock_guard<std::mutex> lk(mu); rcs[wid] = rc; ctx->err = c->err; }
+            const qb200_stats_t &st = c->stats;
+            qb200_stats_t &a = acc[(size_t)wid];
+            a.n_pairs += st.n_pairs; a.kernel_launches += st.kernel_launches; a.word_steps += st.word_steps;
+            a.word_steps_windowed += st.word_steps_windowed; a.word_steps_banded += st.word_steps_banded; a.cells += st.cells;
+            a.h2d_bytes += st.h2d_bytes; a.d2h_bytes += st.d2h_bytes; a.pairs_stage2 += st.pairs_stage2; a.pairs_stage3 += st.pairs_stage3;
+            a.banded_tries += st.banded_tries; a.hirschberg_splits += st.hirschberg_splits; a.leaves += st.leaves;
+            a.ms_total += st.ms_total; a.ms_prepare += st.ms_prepare; a.ms_windowed_s += st.ms_windowed_s; a.ms_windowed_l += st.ms_windowed_l;
+            a.ms_banded += st.ms_banded; a.ms_align_fill += st.ms_align_fill; a.ms_align_trace += st.ms_align_trace; a.ms_cigar += st.ms_cigar;
+            a.matrix_bytes += st.matrix_bytes;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int k = 0; k < NW; ++k) th.emplace_back(worker, k);
+        for (auto &t : th) t.join();
+    }
+    for (int k = 0; k < NW; ++k) if (rcs[k]) return rcs[k];
+    i64 total = 0;
+    for (int q = 0; q < S; ++q) total += std::max<i64>(text_total[(size_t)q], 0);
+    if (res->cigar_off) res->cigar_off[n] = want_cigar ? total : 0;
+    res->cigar_bytes = want_cigar ? total : 0;
+    qb200_stats_t &o = ctx->stats;
+    memset(&o, 0, sizeof o);
+    for (int w = 0; w < NW; ++w) {
+        const qb200_stats_t &a = acc[(size_t)w];
+        o.n_pairs += a.n_pairs; o.kernel_launches += a.kernel_launches; o.word_steps += a.word_steps;
+        o.word_steps_windowed += a.word_steps_windowed; o.word_steps_banded += a.word_steps_banded; o.cells += a.cells;
+        o.h2d_bytes += a.h2d_bytes; o.d2h_bytes += a.d2h_bytes; o.pairs_stage2 += a.pairs_stage2; o.pairs_stage3 += a.pairs_stage3;
+        o.banded_tries += a.banded_tries; o.hirschberg_splits += a.hirschberg_splits; o.leaves += a.leaves;
+        o.ms_total += a.ms_total; o.ms_prepare += a.ms_prepare; o.ms_windowed_s += a.ms_windowed_s; o.ms_windowed_l += a.ms_windowed_l;
+        o.ms_banded += a.ms_banded; o.ms_align_fill += a.ms_align_fill; o.ms_align_trace += a.ms_align_trace; o.ms_cigar += a.ms_cigar;
+        o.matrix_bytes += a.matrix_bytes;
+    }
+    ctx->ran = false;       // results live in the caller's buffers, not in this context
+    return capacity_short ? QB200_ERR_CAPACITY : 0;
+}
+
 int qb200_align_batch(qb200_ctx_t *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res)
 {
+    if (!ctx || !params || !b || !res) return QB200_ERR_ARG;
+    if (b->n_pairs >= 200000 && !getenv("QB200_NO_PIPELINE")) return align_batch_pipelined(ctx, params, b, res);
     int rc = qb200_upload(ctx, b);
     if (rc) return rc;
     rc = qb200_run(ctx, params);

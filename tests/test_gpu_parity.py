@@ -180,3 +180,24 @@ def test_cigars_replay_and_ragged(gpu, oracle):
         for (p, t), g in zip(pairs, got):
             assert g == oracle.align(p, t, algo=algo, bandwidth=30)
             assert replay(expand_rle(g[2]), p.decode(), t.decode()) == g[1]
+
+
+def test_pipelined_align_batch_matches_resident_path(gpu):
+    """qb200_align_batch cuts big batches into double-buffered sub-batches; results must be identical and in order"""
+    import ctypes as C
+    import quicked_b200 as qb
+    n = 230000
+    seqs, po, pl, to, tl = qb.generate_pairs_native(5, n, 100, 0.05)
+    gpu.upload_arrays(seqs, po, pl, to, tl)
+    gpu.run(algo=0)
+    status, score, off, cig = gpu.download()
+    lib = qb.load()
+    score2 = np.empty(n, np.int32); status2 = np.empty(n, np.int32); off2 = np.zeros(n + 1, np.int64)
+    cig2 = np.zeros(int(cig.size), np.uint8)
+    batch = qb.capi.Batch(seqs.ctypes.data, int(seqs.size), n, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data)
+    res = qb.capi.Results(score2.ctypes.data, status2.ctypes.data, cig2.ctypes.data, int(cig2.size), off2.ctypes.data, 0)
+    p = qb.make_params(algo=0)
+    assert lib.qb200_align_batch(gpu._h, C.byref(p), C.byref(batch), C.byref(res)) == 0
+    assert np.array_equal(score, score2) and np.array_equal(status, status2)
+    assert np.array_equal(off, off2) and res.cigar_bytes == cig.size
+    assert np.array_equal(cig, cig2)

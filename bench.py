@@ -57,8 +57,10 @@ class ClockSampler:
         self.idx, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
+        if self.idx is None:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "250",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -210,7 +212,8 @@ def main():
     gpu.upload_arrays(pinned, po, pl, to, tl)
     for _ in range(args.warmup):
         gpu.run(params)
-    sampler = ClockSampler(local_rank)
+    # one sampler per rank on its own GPU; QB_NO_SMI=1 disables it (nvidia-smi polling can perturb short steps)
+    sampler = ClockSampler(None if os.environ.get("QB_NO_SMI") else local_rank)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

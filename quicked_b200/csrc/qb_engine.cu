@@ -508,7 +508,9 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         Span sp(ctx, ST_WS);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * kWsCtasPerSm);   // persistent: one wave
+        int ctas = kWsResidentCtas;
+        if (const char *e = getenv("QB200_WS_CTAS")) ctas = std::max(1, std::min(atoi(e), (int)kWsCtasPerSm));
+        const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * ctas);   // persistent: one wave
         CK(ctx->d_quad.reserve((size_t)blocks * kWsThreads * kWsQuadSlots * 8));
         if (prm.force_scalar)
             k_windowed21_score<false><<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),

@@ -18,8 +18,36 @@
 namespace qb {
 
 constexpr int kWsThreads = 128;                 // threads per CTA of the WindowEd(S) kernel
-constexpr int kWsCtasPerSm = 6;                 // 768 resident threads per SM (register budget 85 per thread)
+constexpr int kWsCtasPerSm = 6;                 // up to 768 resident threads per SM (register budget 85 per thread)
+constexpr int kWsResidentCtas = 4;              // CTAs per SM actually launched (scratch = 16.6 KB per resident CTA-thread group)
 constexpr int kWsQuadSlots = 65 * 2;            // u64 slots per thread in the quadrant scratch ([slot][thread] layout)
+
+// Eight columns of a FULL window (2 words x 128 columns, walk quadrant = word 1 of columns 64..128), the case of all
+// but the first/last windows of a pair.  MODE 0: nothing is stored, 1: columns >= 63 are stored, 2: all are stored.
+template <bool SSE, int MODE>
+__device__ __forceinline__ void ws_full_group8(const unsigned char *__restrict__ tcp, int c0, u32 top_in, const u64 *weq,
+                                               u64 &pv0, u64 &mv0, u64 &pv1, u64 &mv1, u64 &pv1_prev, u64 &mv1_prev,
+                                               u64 *qpv, u64 *qmv, i64 nthr)
+{
+    constexpr int T = kWsThreads;
+    u32 cd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cd[k] = (u32)tcp[k];          // eight independent loads in flight
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        u32 hp_in0 = top_in;
+        if (SSE) hp_in0 = (c == 0) ? top_in : ((c == 1) ? 1u : (u32)((k & 1) ^ 1));   // c0 is a multiple of 8: parity(c) = parity(k)
+        u32 hp, hm, o1, o2;
+        myers_step(weq[cd[k] * T], pv0, mv0, hp_in0, 0u, hp, hm);
+        if (SSE && c == 127) { pv1_prev = pv1; mv1_prev = mv1; }
+        myers_step(weq[(kAlpha + cd[k]) * T], pv1, mv1, hp, hm, o1, o2);
+        if (MODE == 2 || (MODE == 1 && c >= 63)) {
+            qpv[(i64)(c - 63) * nthr] = pv1;
+            qmv[(i64)(c - 63) * nthr] = mv1;
+        }
+    }
+}
 
 template <bool SSE>
 __global__ void __launch_bounds__(kWsThreads, kWsCtasPerSm)
@@ -77,7 +105,16 @@ k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigne
                     qpv[0] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
                     qmv[0] = 0;
                 }
-                for (int c0 = 0; c0 < cols; c0 += 8) {
+                const bool full = (words == 2 && cols == 128 && cv >= 127);      // => r0 == 64, cs == 64
+                if (full) {
+                    const unsigned char *tcp = tc + h0;
+                    for (int c0 = 0; c0 < 56; c0 += 8)
+                        ws_full_group8<SSE, 0>(tcp + c0, c0, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+                    ws_full_group8<SSE, 1>(tcp + 56, 56, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+                    for (int c0 = 64; c0 < 128; c0 += 8)
+                        ws_full_group8<SSE, 2>(tcp + c0, c0, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+                }
+                for (int c0 = full ? cols : 0; c0 < cols; c0 += 8) {
                     // eight independent byte loads in flight instead of one dependent load per column
                     u32 cd[8];
 #pragma unroll

@@ -154,7 +154,7 @@ def main():
         # ~600 us/pair-thread at 10 kbp, ~50 us at 1 kbp, ~6 us at 100 bp: size each step for a few seconds
         per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000}[args.workload]
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample or int(max(cores, min(n_pairs, 4e6 * cores / per_pair_us)))
+        sample = args.cpu_sample or int(max(cores, min(n_pairs, 1e6 * cores / per_pair_us)))
         vals = []
         for s in range(args.warmup + args.steps):
             if s < args.warmup and s > 0:

@@ -139,7 +139,12 @@ static void band_column(band_t *b, const pat_t *p, int code, const uint64_t *pv_
         const int64_t blk = i + b->pos_v;
         uint64_t pv = pv_src[i], mv = mv_src[i];
         unsigned hpo, hmo;
-        myers_block(p->peq[blk * ALPHA + code], &pv, &mv, hp, hm, p->lvl[blk], &hpo, &hmo);
+        /* blocks past the pattern: the reference reads whatever follows its PEQ table there (in-allocation garbage,
+         * SURVEY App. B.4).  One block past is harmless (never read back); further out the garbage reaches the cut
+         * tests, so the reference is undefined.  We define every such block as "no match, carry at bit 63". */
+        const int past = blk >= p->nblk + 2;
+        if (blk > p->nblk) g_ref_undefined = 1;
+        myers_block(past ? 0 : p->peq[blk * ALPHA + code], &pv, &mv, hp, hm, past ? (1ull << 63) : p->lvl[blk], &hpo, &hmo);
         pv_dst[i] = pv; mv_dst[i] = mv;
         hp = hpo; hm = hmo;
         b->scores[blk] += (int64_t)hpo - (int64_t)hmo;

@@ -103,7 +103,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
             ob[r] = (blk == nblk - 1 && mmod) ? mmod - 1 : 63;      // level_mask, bpm_banded.c:88-102
 #pragma unroll
             for (int c = 0; c < kAlpha; ++c)
-                s_eq[(r * kAlpha + c) * 32 + lane] = act ? pq[(i64)c * tk.nbp + blk] : 0ull;
+                s_eq[(r * kAlpha + c) * 32 + lane] = (act && blk < tk.nbp) ? pq[(i64)c * tk.nbp + blk] : 0ull;   // past the table: no match
         }
         __syncwarp();
         const int live = last - first + 1;
@@ -130,7 +130,9 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
                 u64 mh = pv[r] & xh;
                 const u32 HP = __ballot_sync(kFull, (ph >> 63) != 0);
                 const u32 hp_in = lane ? ((HP >> (lane - 1)) & 1u) : hp_carry;
-                sc[r] += (int)((ph >> ob[r]) & 1ull) - (int)((mh >> ob[r]) & 1ull);   // :260
+                sc[r] += (int)(ph >> 63) - (int)(mh >> 63);                            // :260, carry-out at bit 63 ...
+                if (ob[r] != 63)                                                       // ... except the last pattern block (level_mask)
+                    sc[r] += ((int)((ph >> ob[r]) & 1ull) - (int)((mh >> ob[r]) & 1ull)) - ((int)(ph >> 63) - (int)(mh >> 63));
                 ph = (ph << 1) | (u64)hp_in;
                 mh = (mh << 1) | (u64)my_c;
                 const u64 xv = eq | mv[r];
@@ -365,7 +367,7 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
         tk.mat_off -= mat_sub;
         const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
         const int B = (int)g.Bc, prolog = (int)g.prolog;
-        const int nblk = (tk.m + 63) >> 6, clamp = nblk - 1;
+        const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63, clamp = nblk - 1;
         const i64 fin = g.fin, kcut = g.k;
         const u64 *pq = peq + tk.peq_off;
         const unsigned char *tcodes = codes + tk.t_off;
@@ -392,9 +394,8 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
                         s_eq[(j * kAlpha + c) * T] = (blk < tk.nbp) ? pq[(i64)c * tk.nbp + blk] : 0ull;
                 }
             }
-            // In full-matrix mode the level mask of the last pattern block (bpm_banded.c:88-102) can be ignored: it only
-            // changes the carry into rows >= m (never visited by the traceback) and the running score of blocks that
-            // the cut tests never look at (the bottom clamp keeps them out), so every block uses the bit-63 carry.
+            // band index of the last pattern block when its carry-out sits below bit 63 (level_mask, bpm_banded.c:88-102)
+            const int jl = mmod ? (nblk - 1 - pos_v) : -1;
             for (int c0 = 0; c0 < nc; c0 += 8) {
                 u32 cd[8];                                  // eight independent code loads in flight
 #pragma unroll
@@ -412,8 +413,11 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
                         for (int j = 0; j < BMAX; ++j) {
                             if (j >= first && j <= last) {
                                 u32 hpo, hmo;
-                                myers_step(s_eq[(j * kAlpha + code) * T], pv[j], mv[j], hp, hm, hpo, hmo);
-                                sc[j] += (int)hpo - (int)hmo;
+                                u64 phr, mhr;
+                                myers_step_hv(s_eq[(j * kAlpha + code) * T], pv[j], mv[j], hp, hm, hpo, hmo, phr, mhr);
+                                int d = (int)hpo - (int)hmo;
+                                if (j == jl) d = (int)((phr >> (mmod - 1)) & 1ull) - (int)((mhr >> (mmod - 1)) & 1ull);
+                                sc[j] += d;
                                 hp = hpo; hm = hmo;
                                 dst[j * wsd] = make_ulonglong2(pv[j], mv[j]);
                             }

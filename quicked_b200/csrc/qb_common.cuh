@@ -124,6 +124,24 @@ __device__ __forceinline__ void myers_step(u64 eq, u64 &pv, u64 &mv, u32 hp_in, 
     mv = ph & xv;
 }
 
+// Bit-63 update that also hands back the pre-shift horizontal deltas (for a level-masked score, bpm_commons.h:60-61).
+__device__ __forceinline__ void myers_step_hv(u64 eq, u64 &pv, u64 &mv, u32 hp_in, u32 hm_in, u32 &hp_out, u32 &hm_out,
+                                              u64 &ph_raw, u64 &mh_raw)
+{
+    const u64 xv = eq | mv;
+    const u64 eqh = eq | (u64)hm_in;
+    const u64 xh = (((eqh & pv) + pv) ^ pv) | eqh;
+    u64 ph = mv | ~(xh | pv);
+    u64 mh = pv & xh;
+    ph_raw = ph; mh_raw = mh;
+    hp_out = (u32)(ph >> 63);
+    hm_out = (u32)(mh >> 63);
+    ph = (ph << 1) | (u64)hp_in;
+    mh = (mh << 1) | (u64)hm_in;
+    pv = mh | ~(xv | ph);
+    mv = ph & xv;
+}
+
 // Same update, carry-out taken at bit `ob` (reference bpm_commons.h:49-68 with level_mask = 1<<ob).
 __device__ __forceinline__ void myers_step_at(u64 eq, u64 &pv, u64 &mv, u32 hp_in, u32 hm_in, int ob,
                                               u32 &hp_out, u32 &hm_out)

@@ -42,9 +42,11 @@ def test_quicked_matches_oracle(gpu, oracle, length, error, num):
     assert check_against_oracle(gpu, oracle, pairs, algo=0, force_scalar=True) == num
 
 
-@pytest.mark.parametrize("bandwidth", [5, 15, 20, 40])
+@pytest.mark.parametrize("bandwidth", [5, 15, 20, 40, 150, 400])
 def test_banded_matches_oracle(gpu, oracle, bandwidth):
-    for length, error, num in [(100, 0.05, 100), (1000, 0.1, 60), (10000, 0.2, 8)]:
+    for length, error, num in [(100, 0.05, 100), (1000, 0.1, 60), (10000, 0.2, 8), (40, 0.1, 60), (150, 0.3, 60)]:
+        if bandwidth > 100 and length > 1000:
+            continue
         pairs = generate_pairs(num, length, error, seed=3000 + length)
         check_against_oracle(gpu, oracle, pairs, algo=2, bandwidth=bandwidth)
 

@@ -203,3 +203,26 @@ def test_pipelined_align_batch_matches_resident_path(gpu):
     assert np.array_equal(score, score2) and np.array_equal(status, status2)
     assert np.array_equal(off, off2) and res.cigar_bytes == cig.size
     assert np.array_equal(cig, cig2)
+
+
+def test_cli_matches_oracle_output_format(gpu, oracle, tmp_path):
+    """tools/qb_align_benchmark: same flags / .seq input / `score<TAB>CIGAR` output as the reference's align_benchmark
+    (reference tools/align_benchmark/benchmark/benchmark_utils.c:151-170)."""
+    import subprocess
+    from quicked_b200.datagen import write_seq_file
+    from _common import ROOT
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=True)
+    pairs = generate_pairs(300, 500, 0.1, seed=21) + generate_pairs(20, 5000, 0.2, seed=22)
+    seq = tmp_path / "in.seq"
+    write_seq_file(str(seq), pairs)
+    for algo, kw, extra in [("quicked", dict(algo=0), []), ("edit-banded", dict(algo=2, bandwidth=20), ["--bandwidth", "20"]),
+                            ("edit-windowed", dict(algo=1), []), ("edit-banded-hirschberg", dict(algo=3, bandwidth=20), ["--bandwidth", "20"])]:
+        out = tmp_path / f"{algo}.out"
+        r = subprocess.run([os.path.join(ROOT, "tools", "qb_align_benchmark"), "-a", algo, "-i", str(seq), "-o", str(out), "--check", "correct",
+                            "--batch-size", "128"] + extra, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        lines = out.read_text().splitlines()
+        assert len(lines) == len(pairs)
+        for (p, t), line in zip(pairs, lines):
+            st, sc, cg = oracle.align(p, t, **kw)
+            assert line == f"{sc}\t{cg}", (algo, line[:60])

@@ -107,6 +107,13 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
         }
         __syncwarp();
         const int live = last - first + 1;
+        // does any live lane hold the last pattern block with a carry-out below bit 63 (level_mask)?  warp-uniform
+        bool any_masked = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) any_masked |= (first + 32 * r + lane <= last) && ob[r] != 63;
+        any_masked = __any_sync(kFull, any_masked);
+        // running store pointer of this lane's word in the current column (entries; +B per column)
+        ulonglong2 *col_ptr = FULL ? matrix + tk.mat_off + (i64)(col0 + 1) * B + first + lane : nullptr;
         // ---- the column loop ----
         for (int c = 0; c < nc; ++c) {
             const int code = s_txt[c];
@@ -131,18 +138,18 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
                 const u32 HP = __ballot_sync(kFull, (ph >> 63) != 0);
                 const u32 hp_in = lane ? ((HP >> (lane - 1)) & 1u) : hp_carry;
                 sc[r] += (int)(ph >> 63) - (int)(mh >> 63);                            // :260, carry-out at bit 63 ...
-                if (ob[r] != 63)                                                       // ... except the last pattern block (level_mask)
+                if (any_masked && ob[r] != 63)                                         // ... except the last pattern block (level_mask)
                     sc[r] += ((int)((ph >> ob[r]) & 1ull) - (int)((mh >> ob[r]) & 1ull)) - ((int)(ph >> 63) - (int)(mh >> 63));
                 ph = (ph << 1) | (u64)hp_in;
                 mh = (mh << 1) | (u64)my_c;
                 const u64 xv = eq | mv[r];
                 pv[r] = mh | ~(xv | ph);
                 mv[r] = ph & xv;
-                if (store_col && act)
-                    matrix[tk.mat_off + (i64)(col0 + c + 1) * B + j] = make_ulonglong2(pv[r], mv[r]);
+                if (store_col && act) col_ptr[32 * r] = make_ulonglong2(pv[r], mv[r]);
                 cin = (u32)(sum >> 32);
                 hp_carry = HP >> 31;
             }
+            if (FULL) col_ptr += B;
         }
         ws += (u64)live * nc;
         // ---- write the lane's blocks back ----

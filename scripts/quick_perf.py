@@ -6,7 +6,7 @@ import time
 sys.path.insert(0, ".")
 import quicked_b200 as qb  # noqa: E402
 
-CONFIGS = {"c1": (100, 0.05, 100000), "c2": (1000, 0.10, 200000), "c3": (10000, 0.20, 10000), "c2s": (1000, 0.10, 20000)}
+CONFIGS = {"c1": (100, 0.05, 100000), "c2": (1000, 0.10, 200000), "c3": (10000, 0.20, 10000), "c2s": (1000, 0.10, 20000), "c4": (100000, 0.20, 256)}
 
 
 def main():

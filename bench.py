@@ -204,6 +204,7 @@ def main():
     pin = lib.qb200_host_alloc(seqs.size)
     pinned = np.ctypeslib.as_array(C.cast(pin, C.POINTER(C.c_uint8)), shape=(seqs.size,))
     pinned[:] = seqs
+    del seqs                          # keep one host copy per rank (8 ranks share the box's RAM)
     stream = torch.cuda.current_stream().cuda_stream
     gpu = qb.BatchAligner(device=local_rank, stream=stream)
     params = qb.make_params(**algo_kw)

@@ -226,3 +226,31 @@ def test_cli_matches_oracle_output_format(gpu, oracle, tmp_path):
         for (p, t), line in zip(pairs, lines):
             st, sc, cg = oracle.align(p, t, **kw)
             assert line == f"{sc}\t{cg}", (algo, line[:60])
+
+
+def test_cpp_binding_example(tmp_path):
+    """include/quicked.hpp: the reference's C++ binding surface (bindings/cpp/quicked.hpp:46-73) + alignMany"""
+    import subprocess
+    from _common import ROOT
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools"), "example_binding"], check=True)
+    r = subprocess.run([os.path.join(ROOT, "tools", "example_binding")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines() == ["Score: 1", "Cigar: 2M1X1M", "1\t3M1X3M", "1\t4M1D3M"]
+
+
+def test_upload_device_path(gpu, oracle):
+    """qb200_upload_device: the packed batch already lives in HBM (torch tensors), no host copy of the characters"""
+    import torch
+    import quicked_b200 as qb
+    pairs = generate_pairs(300, 700, 0.1, seed=33)
+    seqs, po, pl, to, tl = qb.pack_pairs(pairs)
+    pad = (-len(seqs)) % 16
+    seqs = np.concatenate([seqs, np.zeros(pad, np.uint8)])
+    d = [torch.from_numpy(a).cuda() for a in (seqs, po, pl, to, tl)]
+    torch.cuda.synchronize()
+    gpu.upload_device_ptrs(d[0].data_ptr(), int(seqs.size), len(pairs), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr())
+    gpu.run(algo=0)
+    status, score, off, cig = gpu.download()
+    raw = cig.tobytes()
+    for i, (p, t) in enumerate(pairs):
+        assert (int(status[i]), int(score[i]), raw[off[i]:off[i + 1] - 1].decode()) == oracle.align(p, t)

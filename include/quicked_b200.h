@@ -67,6 +67,9 @@ typedef struct {                  /* counters of the last qb200_run(); all times
     float   ms_total, ms_prepare, ms_windowed_s, ms_windowed_l, ms_banded, ms_align_fill, ms_align_trace,
             ms_cigar;
     int64_t matrix_bytes;         /* traceback state written to HBM (Pv/Mv columns)                        */
+    float   ms_fused;             /* the fused WindowEd+BandEd+traceback kernel of the QUICKED fast path   */
+    int32_t pad_;
+    int64_t pairs_fused;          /* pairs completed by that kernel                                        */
 } qb200_stats_t;
 
 /* --- context --- */

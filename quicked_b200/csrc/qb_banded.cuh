@@ -348,39 +348,18 @@ k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ li
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// k_banded_thread<BMAX>: full-matrix BandEd for NARROW bands (B_cigar <= BMAX blocks), ONE LEAF PER THREAD.
-//
-// At 100 bp - 1 kbp and <= 10 % error the band is 3 blocks tall: a warp-per-pair mapping would idle 29 lanes, so
-// here each thread carries its whole band (Pv, Mv, running scores) in registers and walks the blocks of a column
-// serially exactly like the reference's inner loop (bpm_banded.c:238-261) — no cross-lane traffic at all.
-// The 32 leaves of a warp are interleaved in the matrix: entry (column c, band word w, lane l) lives at
-// group_base + (c*Bg + w)*32 + l, so every (Pv,Mv) store of the warp is one coalesced 512-byte line group.
-// The lane's 5 match masks per live block are staged in shared memory ([slot][thread], conflict-free) once per
-// 64 columns; the per-column fetch is an LDS indexed by the column's code.
+// Full-matrix BandEd of ONE leaf by one thread (see k_banded_thread).  mat: first entry of this leaf, column stride
+// cs / word stride wsd (entries); ranges: live range per 64-column block, stride rstride; s_eq: this thread's
+// BMAX*5 shared-memory slots, stride T.
 template <int BMAX>
-__global__ void __launch_bounds__(128, 5)
-k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
-                const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
-                int2 *__restrict__ range_pool, u64 *__restrict__ counters)
+__device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int rev, const u64 *__restrict__ pq, int nbp,
+                                                   const unsigned char *__restrict__ tcodes, ulonglong2 *mat, i64 cs, i64 wsd,
+                                                   int2 *ranges, i64 rstride, u64 *s_eq, int T, u64 &ws)
 {
-    extern __shared__ u64 s_eq_all[];                       // [BMAX*5][blockDim.x]
-    const int T = blockDim.x, tid = threadIdx.x;
-    u64 *s_eq = s_eq_all + tid;
-    const int id = blockIdx.x * T + tid;
-    u64 ws = 0;
-    if (id < n_tasks) {
-        BandTask tk = tasks[list ? list[begin + id] : begin + id];
-        tk.mat_off -= mat_sub;
-        const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+        const BandGeom g = band_geometry(m, n, cutoff);
         const int B = (int)g.Bc, prolog = (int)g.prolog;
-        const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63, clamp = nblk - 1;
+        const int nblk = (m + 63) >> 6, mmod = m & 63, clamp = nblk - 1;
         const i64 fin = g.fin, kcut = g.k;
-        const u64 *pq = peq + tk.peq_off;
-        const unsigned char *tcodes = codes + tk.t_off;
-        ulonglong2 *mat = matrix + tk.mat_off;
-        const i64 cs = tk.mat_cs, wsd = tk.mat_ws;
-        int2 *ranges = range_pool + tk.range_off;
         int first = prolog, last = B - 1, pos_v = -prolog, pos_h = 0;
         u64 pv[BMAX], mv[BMAX];
         int sc[BMAX];
@@ -390,15 +369,15 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
             if (j < B) mat[j * wsd] = make_ulonglong2(~0ull, 0ull);               // column 0
         }
         ranges[0] = make_int2(first, last);
-        for (int col0 = 0; col0 < tk.n; col0 += 64) {
-            const int nc = min(64, tk.n - col0);
+        for (int col0 = 0; col0 < n; col0 += 64) {
+            const int nc = min(64, n - col0);
 #pragma unroll
             for (int j = 0; j < BMAX; ++j) {
                 const int blk = j + pos_v;
                 if (j >= first && j <= last) {
 #pragma unroll
                     for (int c = 0; c < kAlpha; ++c)
-                        s_eq[(j * kAlpha + c) * T] = (blk < tk.nbp) ? pq[(i64)c * tk.nbp + blk] : 0ull;
+                        s_eq[(j * kAlpha + c) * T] = (blk < nbp) ? pq[(i64)c * nbp + blk] : 0ull;
                 }
             }
             // band index of the last pattern block when its carry-out sits below bit 63 (level_mask, bpm_banded.c:88-102)
@@ -408,7 +387,7 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int col = col0 + c0 + k;
-                    cd[k] = (c0 + k < nc) ? (u32)(tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col]) : 4u;
+                    cd[k] = (c0 + k < nc) ? (u32)(rev ? tcodes[n - 1 - col] : tcodes[col]) : 4u;
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -463,8 +442,36 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
             const bool cut_hi = (first + 2 < last) && (64 * (i64)(last - 1) > fin) && ((i64)s_l1 + (64 * (i64)(last - 1) - fin) > kcut);
             if (cut_hi || (pos_v + last >= clamp)) --last;
             ++pos_v; ++pos_h;
-            ranges[pos_h] = make_int2(first, last);
+            ranges[(i64)pos_h * rstride] = make_int2(first, last);
         }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_banded_thread<BMAX>: full-matrix BandEd for NARROW bands (B_cigar <= BMAX blocks), ONE LEAF PER THREAD.
+//
+// At 100 bp - 1 kbp and <= 10 % error the band is 3 blocks tall: a warp-per-pair mapping would idle 29 lanes, so
+// here each thread carries its whole band (Pv, Mv, running scores) in registers and walks the blocks of a column
+// serially exactly like the reference's inner loop (bpm_banded.c:238-261) — no cross-lane traffic at all.
+// The 32 leaves of a warp are interleaved in the matrix: entry (column c, band word w, lane l) lives at
+// group_base + (c*Bg + w)*32 + l, so every (Pv,Mv) store of the warp is one coalesced 512-byte line group.
+// The lane's 5 match masks per live block are staged in shared memory ([slot][thread], conflict-free) once per
+// 64 columns; the per-column fetch is an LDS indexed by the column's code.
+template <int BMAX>
+__global__ void __launch_bounds__(128, 5)
+k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
+                const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
+                int2 *__restrict__ range_pool, u64 *__restrict__ counters)
+{
+    extern __shared__ u64 s_eq_all[];                       // [BMAX*5][blockDim.x]
+    const int T = blockDim.x, tid = threadIdx.x;
+    u64 *s_eq = s_eq_all + tid;
+    const int id = blockIdx.x * T + tid;
+    u64 ws = 0;
+    if (id < n_tasks) {
+        BandTask tk = tasks[list ? list[begin + id] : begin + id];
+        tk.mat_off -= mat_sub;
+        banded_thread_fill<BMAX>(tk.m, tk.n, tk.cutoff, tk.rev, peq + tk.peq_off, tk.nbp, codes + tk.t_off, matrix + tk.mat_off,
+                                 tk.mat_cs, tk.mat_ws, range_pool + tk.range_off, 1, s_eq, T, ws);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ws += __shfl_down_sync(kFull, ws, o);

@@ -25,6 +25,7 @@ struct PairRec {
     i64 peq_off;          // u64 index of the forward match-mask table in the PEQ pool ([code][nbp] layout)
     int nbp;              // blocks in that table = ceil(m/64) + 2 (two all-zero blocks appended)
     int pad_;
+    i64 ops_off;          // u32 index of this pair's 2-bit op words in the fused-path region of the op pool
 };
 
 // One BandEd work item: a score-only pass or a full-matrix leaf over a sub-rectangle of a pair.

@@ -21,6 +21,7 @@
 
 #include "qb_banded.cuh"
 #include "qb_common.cuh"
+#include "qb_fused.cuh"
 #include "qb_hirschberg.cuh"
 #include "qb_plan.cuh"
 #include "qb_prep.cuh"
@@ -69,7 +70,7 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum Stage { ST_PREP = 0, ST_WS, ST_WL, ST_BANDED, ST_FILL, ST_TRACE, ST_CIGAR, ST_PLAN, ST_COUNT };
+enum Stage { ST_PREP = 0, ST_WS, ST_WL, ST_BANDED, ST_FILL, ST_TRACE, ST_CIGAR, ST_PLAN, ST_FUSED, ST_COUNT };
 
 }  // namespace
 
@@ -93,6 +94,9 @@ struct qb200_ctx {
     DevBuf d_cls, d_cutoff, d_plan_items, d_plan_offs, d_textbytes, d_list_t, d_list_w, d_list_slow, d_gsize, d_goff, d_gB;
     unsigned char *h_pinned = nullptr;     // small pinned mailbox for totals
     DevBuf d_quad;                         // WindowEd(S) quadrant scratch
+    DevBuf d_fmat, d_franges, d_done;      // fused fast path: per-resident-warp matrix slots, live ranges, per-pair done flags
+    i64 ops_words_fused = 0;               // op words of all pairs (fused-path region of the op pool)
+    int max_n = 0;
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
     static constexpr int kWorkers = 8;
@@ -168,7 +172,8 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
     ctx->h_pairs.resize((size_t)n);
     ctx->h_peqjobs.clear();
     ctx->h_peqjobs.reserve((size_t)n);
-    i64 words = 0, cells = 0;
+    i64 words = 0, cells = 0, ops_words = 0;
+    int max_n = 0;
     for (i64 i = 0; i < n; ++i) {
         PairRec &r = ctx->h_pairs[(size_t)i];
         r.p_off = poff[i]; r.t_off = toff[i]; r.m = plen[i]; r.n = tlen[i];
@@ -179,7 +184,10 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
         r.nbp = (r.m + 63) / 64 + 2;
         r.peq_off = words;
         r.pad_ = 0;
+        r.ops_off = ops_words;
         if (r.m > 0 && r.n > 0) {
+            ops_words += (r.m + r.n + 15) / 16;
+            max_n = std::max(max_n, r.n);
             PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = words;
             ctx->h_peqjobs.push_back(j);
             words += (i64)kAlpha * r.nbp;
@@ -188,6 +196,8 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
     }
     ctx->peq_words = words;
     ctx->cells = cells;
+    ctx->ops_words_fused = ops_words;
+    ctx->max_n = max_n;
     return 0;
 }
 
@@ -366,7 +376,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
                       &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
                       &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB, &ctx->d_peq2, &ctx->d_jobs2, &ctx->d_tasks2, &ctx->d_wintasks,
-                      &ctx->d_quad, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter})
+                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -503,8 +513,53 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         }
     }
 
+    // ---- QUICKED fast path: one fused kernel (WindowEd(S) -> BandEd fill -> traceback) for narrow-band pairs ----
+    // Measured on B200 (profiles/README.md): the fused kernel wins on small, launch-bound jobs (100 bp x 100 k pairs:
+    // 0.70 vs 1.09 ms) and needs no 48 GB traceback pool; on big batches three specialised kernels are ~10 % faster.
+    bool use_fused = (prm.algo == QUICKED) && ctx->raw_bytes < ((i64)64 << 20);
+    if (const char *e = getenv("QB200_FUSED")) use_fused = (prm.algo == QUICKED) && atoi(e) != 0;
+    i64 leaf_base = 0, ops_base = 0;
+    if (use_fused) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        int fctas = kFusedCtasPerSm;
+        if (const char *e = getenv("QB200_FUSED_CTAS")) fctas = std::max(1, std::min(atoi(e), (int)kFusedCtasPerSm));
+        const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * fctas);   // persistent: one wave
+        const i64 nthr = (i64)blocks * kWsThreads, warps = nthr / 32;
+        const i64 budget = (i64)std::min<size_t>(ctx->matrix_limit, (size_t)24 << 30);
+        const i64 n_cap = budget / (warps * kFusedBandMax * 32 * 16) - 1;
+        FusedParams fp;
+        fp.hew_threshold0 = (int)prm.hew_threshold[0]; fp.hew_pct0 = prm.hew_percentage[0];
+        fp.n_lim = (int)std::max<i64>(0, std::min<i64>(ctx->max_n, n_cap));
+        fp.ok_status = QUICKED_WIP;
+        fp.mat_warp_stride = (i64)(fp.n_lim + 1) * kFusedBandMax * 32;
+        CK(ctx->d_quad.reserve((size_t)nthr * kWsQuadSlots * 8));
+        CK(ctx->d_fmat.reserve((size_t)warps * (size_t)fp.mat_warp_stride * 16));
+        CK(ctx->d_franges.reserve((size_t)(fp.n_lim / 64 + 2) * (size_t)nthr * 8));
+        CK(ctx->d_done.reserve((size_t)n));
+        CK(ctx->d_leaves.reserve(sizeof(BandTask) * (size_t)n));
+        CK(ctx->d_leafout.reserve(sizeof(LeafOut) * (size_t)n));
+        CK(ctx->d_ops.reserve((size_t)std::max<i64>(ctx->ops_words_fused, 1) * 4 + 16));
+        {
+            Span sp(ctx, ST_FUSED);
+            if (prm.force_scalar)
+                k_quicked_fused<false><<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                    ctx->d_peq.as<u64>(), fp, ctx->d_quad.as<u64>(), ctx->d_fmat.as<ulonglong2>(), ctx->d_franges.as<int2>(), ctx->d_ops.as<u32>(),
+                    ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_done.as<unsigned char>(), ctx->d_status.as<int>(), ctx->d_leaves.as<BandTask>(),
+                    ctx->d_leafout.as<LeafOut>(), ctx->d_pairleaves.as<PairLeaves>(), ctx->d_counters.as<u64>());
+            else
+                k_quicked_fused<true><<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                    ctx->d_peq.as<u64>(), fp, ctx->d_quad.as<u64>(), ctx->d_fmat.as<ulonglong2>(), ctx->d_franges.as<int2>(), ctx->d_ops.as<u32>(),
+                    ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_done.as<unsigned char>(), ctx->d_status.as<int>(), ctx->d_leaves.as<BandTask>(),
+                    ctx->d_leafout.as<LeafOut>(), ctx->d_pairleaves.as<PairLeaves>(), ctx->d_counters.as<u64>());
+            CK(cudaGetLastError());
+            ctx->stats.kernel_launches++;
+        }
+        ctx->stats.matrix_bytes += 0;
+        leaf_base = n; ops_base = ctx->ops_words_fused;
+    }
     // ---- QUICKED stage 1: WindowEd(S) bound (quicked.c:178-199) ----
-    if (prm.algo == QUICKED) {
+    if (prm.algo == QUICKED && !use_fused) {
         Span sp(ctx, ST_WS);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -532,7 +587,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         pp.ok_status = (prm.algo == HIRSCHBERG) ? QUICKED_OK : QUICKED_WIP;
         k_plan<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, pp, ctx->d_bound.as<int>(), ctx->d_hew.as<int>(),
                                                ctx->d_plan_items.as<PlanSum>(), ctx->d_cls.as<unsigned char>(), ctx->d_cutoff.as<i64>(),
-                                               ctx->d_status.as<int>(), ctx->d_score.as<int>());
+                                               ctx->d_status.as<int>(), ctx->d_score.as<int>(), use_fused ? ctx->d_done.as<unsigned char>() : nullptr);
         CK(cudaGetLastError());
         size_t tmp = 0;
         const PlanSum zero = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -549,17 +604,18 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     const PlanSum &tot = plan.tot;
 
     // ---- slow path first (it appends its leaves after the fast ones and returns its pool usage) ----
-    i64 n_leaves = tot.leaf, ops_words = tot.ops, range_ints = tot.rng;
+    i64 n_leaves = leaf_base + tot.leaf, ops_words = ops_base + tot.ops, range_ints = tot.rng;
     std::vector<PairLeaves> slow_pl;
     std::vector<int> slow_pairs;
     if (tot.slow > 0) {
         slow_pairs.resize((size_t)tot.slow);
     }
-    CK(ctx->d_leaves.reserve(sizeof(BandTask) * (size_t)std::max<i64>(n_leaves, 1)));
-    if (tot.leaf > 0 || tot.slow > 0) {
+    CK(ctx->d_leaves.grow_keep(sizeof(BandTask) * (size_t)std::max<i64>(n_leaves, 1), sizeof(BandTask) * (size_t)leaf_base, ctx->stream));
+    {   // every pair not finished by the fused kernel gets its leaf list (possibly empty) here
         k_build_leaves<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_cls.as<unsigned char>(), ctx->d_cutoff.as<i64>(),
                                                        ctx->d_plan_offs.as<PlanSum>(), ctx->d_leaves.as<BandTask>(), ctx->d_list_t.as<int>(),
-                                                       ctx->d_list_w.as<int>(), ctx->d_list_slow.as<int>(), ctx->d_pairleaves.as<PairLeaves>());
+                                                       ctx->d_list_w.as<int>(), ctx->d_list_slow.as<int>(), ctx->d_pairleaves.as<PairLeaves>(),
+                                                       use_fused ? ctx->d_done.as<unsigned char>() : nullptr, leaf_base, ops_base);
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
     }
@@ -592,9 +648,9 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     }
 
     // pools of the fast path
-    CK(ctx->d_ops.reserve((size_t)std::max<i64>(ops_words, 1) * 4 + 16));
+    CK(ctx->d_ops.grow_keep((size_t)std::max<i64>(ops_words, 1) * 4 + 16, (size_t)ops_base * 4, ctx->stream));
     CK(ctx->d_ranges.reserve((size_t)std::max<i64>(range_ints, 1) * 8 + 16));
-    CK(ctx->d_leafout.reserve(sizeof(LeafOut) * (size_t)std::max<i64>(n_leaves, 1)));
+    CK(ctx->d_leafout.grow_keep(sizeof(LeafOut) * (size_t)std::max<i64>(n_leaves, 1), sizeof(LeafOut) * (size_t)leaf_base, ctx->stream));
     CK(ctx->d_bandout.reserve(sizeof(BandOut) * (size_t)std::max<i64>(n_leaves, 1)));
     if (tot.sc > 0) {
         CK(ctx->d_scores.reserve((size_t)tot.sc * 4 + 16));
@@ -717,6 +773,9 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     ctx->stats.ms_prepare = st[ST_PREP] + st[ST_PLAN]; ctx->stats.ms_windowed_s = st[ST_WS]; ctx->stats.ms_windowed_l = st[ST_WL];
     ctx->stats.ms_banded = st[ST_BANDED]; ctx->stats.ms_align_fill = st[ST_FILL]; ctx->stats.ms_align_trace = st[ST_TRACE];
     ctx->stats.ms_cigar = st[ST_CIGAR];
+    ctx->stats.ms_fused = st[ST_FUSED];
+    ctx->stats.pairs_fused = (i64)counters[2];
+    ctx->stats.leaves += (i64)counters[2];
     ctx->ran = true;
     return 0;
 }
@@ -1348,7 +1407,7 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
             a.banded_tries += st.banded_tries; a.hirschberg_splits += st.hirschberg_splits; a.leaves += st.leaves;
             a.ms_total += st.ms_total; a.ms_prepare += st.ms_prepare; a.ms_windowed_s += st.ms_windowed_s; a.ms_windowed_l += st.ms_windowed_l;
             a.ms_banded += st.ms_banded; a.ms_align_fill += st.ms_align_fill; a.ms_align_trace += st.ms_align_trace; a.ms_cigar += st.ms_cigar;
-            a.matrix_bytes += st.matrix_bytes;
+            a.matrix_bytes += st.matrix_bytes; a.ms_fused += st.ms_fused; a.pairs_fused += st.pairs_fused;
         }
     };
     {
@@ -1371,7 +1430,7 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
         o.banded_tries += a.banded_tries; o.hirschberg_splits += a.hirschberg_splits; o.leaves += a.leaves;
         o.ms_total += a.ms_total; o.ms_prepare += a.ms_prepare; o.ms_windowed_s += a.ms_windowed_s; o.ms_windowed_l += a.ms_windowed_l;
         o.ms_banded += a.ms_banded; o.ms_align_fill += a.ms_align_fill; o.ms_align_trace += a.ms_align_trace; o.ms_cigar += a.ms_cigar;
-        o.matrix_bytes += a.matrix_bytes;
+        o.matrix_bytes += a.matrix_bytes; o.ms_fused += a.ms_fused; o.pairs_fused += a.pairs_fused;
     }
     ctx->ran = false;       // results live in the caller's buffers, not in this context
     return capacity_short ? QB200_ERR_CAPACITY : 0;

@@ -48,12 +48,16 @@ __device__ __forceinline__ int rounds_for_dev(i64 B)
 __global__ void __launch_bounds__(256)
 k_plan(const PairRec *__restrict__ pairs, int n, PlanParams pp, const int *__restrict__ bound,
        const int *__restrict__ hew, PlanSum *__restrict__ items, unsigned char *__restrict__ cls,
-       i64 *__restrict__ cutoff, int *__restrict__ status, int *__restrict__ score)
+       i64 *__restrict__ cutoff, int *__restrict__ status, int *__restrict__ score, const unsigned char *__restrict__ done)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const PairRec r = pairs[i];
     PlanSum it = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (done && done[i]) {                                          // finished by the fused kernel
+        items[i] = it; cls[i] = (unsigned char)CLS_NONE; cutoff[i] = 0; score[i] = -1;
+        return;
+    }
     int c = CLS_NONE, st = -1 /* QUICKED_ERROR */;
     i64 cut = 0;
     if (r.m <= 0 || r.n <= 0) {
@@ -100,12 +104,14 @@ __global__ void __launch_bounds__(256)
 k_build_leaves(const PairRec *__restrict__ pairs, int n, const unsigned char *__restrict__ cls,
                const i64 *__restrict__ cutoff, const PlanSum *__restrict__ offs, BandTask *__restrict__ leaves,
                int *__restrict__ list_t, int *__restrict__ list_w, int *__restrict__ list_slow,
-               PairLeaves *__restrict__ pl)
+               PairLeaves *__restrict__ pl, const unsigned char *__restrict__ done, i64 leaf_base, i64 ops_base)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (done && done[i]) return;                                    // the fused kernel already wrote this pair's records
     const int c = cls[i];
-    const PlanSum o = offs[i];
+    PlanSum o = offs[i];
+    o.leaf += leaf_base; o.ops += ops_base;
     PairLeaves p; p.first_leaf = o.leaf; p.n_leaves = 0; p.pad_ = 0;
     if (c == CLS_T || c == CLS_W) {
         const PairRec r = pairs[i];

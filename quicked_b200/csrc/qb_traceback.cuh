@@ -53,28 +53,15 @@ __device__ __forceinline__ bool cell_written(const int2 *ranges, int B, int c, i
     return w >= lo && w <= r.y;
 }
 
-// One leaf per thread.  Works on both matrix layouts (warp kernel: [column][word]; thread kernel: 32 leaves
-// interleaved) through the task's column / word strides.  Per step the walk needs bit v of Pv[column h+1] and of
-// Mv[column h]; (Pv,Mv) of one (column, word) is a single 16-byte entry, so the entry fetched for Mv at column h
-// is reused for Pv when the walk moves to column h-1, and the live ranges are cached per 64-column block:
-// about one 16-byte load per visited column instead of four dependent loads per step.
-__global__ void __launch_bounds__(128)
-k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
-                   const unsigned char *__restrict__ raw, const ulonglong2 *__restrict__ matrix,
-                   const int2 *__restrict__ range_pool, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
+// The walk of ONE leaf by one thread (see k_traceback_thread).
+__device__ __forceinline__ void traceback_walk_thread(int m, int n, i64 cutoff, const ulonglong2 *mat, i64 cs, i64 wsd,
+                                                      const int2 *ranges, i64 rstride, const unsigned char *__restrict__ praw,
+                                                      const unsigned char *__restrict__ traw, u32 *ops, int ops_cap, LeafOut &o)
 {
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= n_tasks) return;
-    BandTask tk = tasks[list ? list[begin + id] : begin + id];
-    tk.mat_off -= mat_sub;
-    const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+    const BandGeom g = band_geometry(m, n, cutoff);
     const int B = (int)g.Bc, prolog = (int)g.prolog;
-    const ulonglong2 *mat = matrix + tk.mat_off;
-    const int2 *ranges = range_pool + tk.range_off;
-    const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
-    const i64 cs = tk.mat_cs, wsd = tk.mat_ws;
-    OpWriter w; w.init(ops_pool + tk.ops_off, tk.ops_cap);
-    int h = tk.n - 1, v = tk.m - 1;
+    OpWriter w; w.init(ops, ops_cap);
+    int h = n - 1, v = m - 1;
     // cached live ranges of column blocks kb_c and kb_c + 1
     int kb_c = -2; int2 rg0 = make_int2(0, -1), rg1 = make_int2(0, -1);
     // cached entries: key = column * B + word (the reference's flat index), -1 = empty
@@ -82,12 +69,12 @@ k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ l
     ulonglong2 eR = make_ulonglong2(0, 0), eL = make_ulonglong2(0, 0);
     auto fetch = [&](int c, int wd) -> ulonglong2 {
         // never-written cells read as 0 (see cell_written); the live range of column c comes from block (c-1)/64
-        if (c < 0 || c > tk.n || wd < 0 || wd >= B) return make_ulonglong2(0, 0);
+        if (c < 0 || c > n || wd < 0 || wd >= B) return make_ulonglong2(0, 0);
         if (c > 0) {
             const int kb = (c - 1) >> 6;
             if (kb != kb_c) {
-                if (kb == kb_c + 1) rg0 = rg1; else rg0 = ranges[kb];
-                rg1 = ranges[kb + 1];
+                if (kb == kb_c + 1) rg0 = rg1; else rg0 = ranges[(i64)kb * rstride];
+                rg1 = ranges[(i64)(kb + 1) * rstride];
                 kb_c = kb;
             }
             const int lo = (c & 63) ? rg0.x : min(rg0.x, rg1.x);
@@ -120,9 +107,27 @@ k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ l
     while (h >= 0) { w.emit(OP_I); --h; }
     while (v >= 0) { w.emit(OP_D); --v; }
     w.finish();
-    LeafOut o;
-    o.n_ops = tk.ops_cap - w.pos; o.cost = w.cost; o.text_len = w.text_len;
+    o.n_ops = ops_cap - w.pos; o.cost = w.cost; o.text_len = w.text_len;
     o.fmt = 0; o.pad_ = 0;
+}
+
+// One leaf per thread.  Works on both matrix layouts (warp kernel: [column][word]; thread kernel: 32 leaves
+// interleaved) through the task's column / word strides.  Per step the walk needs bit v of Pv[column h+1] and of
+// Mv[column h]; (Pv,Mv) of one (column, word) is a single 16-byte entry, so the entry fetched for Mv at column h
+// is reused for Pv when the walk moves to column h-1, and the live ranges are cached per 64-column block:
+// about one 16-byte load per visited column instead of four dependent loads per step.
+__global__ void __launch_bounds__(128)
+k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
+                   const unsigned char *__restrict__ raw, const ulonglong2 *__restrict__ matrix,
+                   const int2 *__restrict__ range_pool, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
+{
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_tasks) return;
+    BandTask tk = tasks[list ? list[begin + id] : begin + id];
+    tk.mat_off -= mat_sub;
+    LeafOut o;
+    traceback_walk_thread(tk.m, tk.n, tk.cutoff, matrix + tk.mat_off, tk.mat_cs, tk.mat_ws, range_pool + tk.range_off, 1,
+                          raw + tk.p_off, raw + tk.t_off, ops_pool + tk.ops_off, tk.ops_cap, o);
     outs[tk.slot] = o;
 }
 

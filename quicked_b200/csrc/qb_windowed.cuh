@@ -49,25 +49,14 @@ __device__ __forceinline__ void ws_full_group8(const unsigned char *__restrict__
     }
 }
 
+// WindowEd(S) of ONE pair by one thread (see k_windowed21_score).  weq: this thread's 10 shared-memory slots
+// (stride kWsThreads); qpv/qmv: this thread's quadrant scratch (slot stride nthr).
 template <bool SSE>
-__global__ void __launch_bounds__(kWsThreads, kWsCtasPerSm)
-k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigned char *__restrict__ codes,
-                   const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, int hew_threshold,
-                   int *__restrict__ bound, int *__restrict__ hew_out, u64 *__restrict__ counters,
-                   u64 *__restrict__ quad)
+__device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char *__restrict__ codes,
+                                          const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, u64 *weq,
+                                          u64 *qpv, u64 *qmv, i64 nthr, int hew_lim, int &score_out, int &hew_out, u64 &ws)
 {
-    __shared__ u64 s_weq[2 * kAlpha * kWsThreads];          // [2*5][T] window-aligned match masks
-    const int T = kWsThreads, t = threadIdx.x;
-    u64 *weq = s_weq + t;
-    const i64 gtid = (i64)blockIdx.x * T + t, nthr = (i64)gridDim.x * T;
-    // Quadrant scratch: [slot][resident thread] in HBM/L2 (reused window after window, pair after pair, so it stays
-    // L2-resident); a shared-memory copy would cap the SM at ~200 threads and leave it latency-bound.
-    u64 *qpv = quad + gtid;                                  // slot s at qpv[s * nthr]
-    u64 *qmv = quad + 65 * nthr + gtid;
-    const int hew_lim = 64 * hew_threshold / 100;            // (W-O)*64*thr/100, bpm_windowed.c:555
-    u64 ws = 0;
-    for (i64 i = gtid; i < n_pairs; i += nthr) {
-        const PairRec pr = pairs[i];
+    constexpr int T = kWsThreads;
         int score = 0, hew = 0;
         int cv = pr.m - 1, ch = pr.n - 1;                    // corner (pos_v,pos_h), bpm_windowed.c:148-149
         if (pr.m > 0 && pr.n > 0) {
@@ -186,6 +175,30 @@ k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigne
             if (ch >= 0) score += ch + 1;      // bpm_windowed.c:599-607
             if (cv >= 0) score += cv + 1;
         }
+        score_out = score; hew_out = hew;
+}
+
+template <bool SSE>
+__global__ void __launch_bounds__(kWsThreads, kWsCtasPerSm)
+k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigned char *__restrict__ codes,
+                   const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, int hew_threshold,
+                   int *__restrict__ bound, int *__restrict__ hew_out, u64 *__restrict__ counters,
+                   u64 *__restrict__ quad)
+{
+    __shared__ u64 s_weq[2 * kAlpha * kWsThreads];          // [2*5][T] window-aligned match masks
+    const int T = kWsThreads, t = threadIdx.x;
+    u64 *weq = s_weq + t;
+    const i64 gtid = (i64)blockIdx.x * T + t, nthr = (i64)gridDim.x * T;
+    // Quadrant scratch: [slot][resident thread] in HBM/L2 (reused window after window, pair after pair, so it stays
+    // L2-resident); a shared-memory copy would cap the SM at ~200 threads and leave it latency-bound.
+    u64 *qpv = quad + gtid;                                  // slot s at qpv[s * nthr]
+    u64 *qmv = quad + 65 * nthr + gtid;
+    const int hew_lim = 64 * hew_threshold / 100;            // (W-O)*64*thr/100, bpm_windowed.c:555
+    u64 ws = 0;
+    for (i64 i = gtid; i < n_pairs; i += nthr) {
+        const PairRec pr = pairs[i];
+        int score = 0, hew = 0;
+        ws21_pair<SSE>(pr, codes, raw, peq, weq, qpv, qmv, nthr, hew_lim, score, hew, ws);
         bound[i] = score;
         hew_out[i] = hew;
     }

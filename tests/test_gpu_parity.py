@@ -254,3 +254,20 @@ def test_upload_device_path(gpu, oracle):
     raw = cig.tobytes()
     for i, (p, t) in enumerate(pairs):
         assert (int(status[i]), int(score[i]), raw[off[i]:off[i + 1] - 1].decode()) == oracle.align(p, t)
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_fused_and_planned_paths_agree(oracle, fused, monkeypatch):
+    """QB200_FUSED forces the single fused kernel / the three specialised kernels of the QUICKED fast path"""
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_FUSED", fused)
+    a = qb.BatchAligner(device=0)
+    pairs = generate_pairs(300, 1000, 0.1, seed=51) + generate_pairs(200, 100, 0.05, seed=52) + generate_pairs(8, 10000, 0.2, seed=53) + \
+        generate_pairs(20, 3000, 0.05, seed=54, indels=(4, 200)) + [("", "ACGT"), ("ACGT", "ACGT")]
+    for fs in (False, True):
+        got = a.align(pairs, algo=0, force_scalar=fs)
+        st = a.stats()
+        assert (st["pairs_fused"] > 400) == (fused == "1")
+        for (p, t), g in zip(pairs, got):
+            assert g == oracle.align(p, t, algo=0, force_scalar=fs)
+    a.close()

@@ -167,8 +167,9 @@ __device__ __forceinline__ u64 funnel_r(u64 lo, u64 hi, unsigned sh)   // (hi:lo
 
 __device__ __forceinline__ int dec_digits(unsigned v)
 {
-    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5
-         : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+    if (v < 100u) return v < 10u ? 1 : 2;               // the common case: short runs
+    return v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7
+         : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
 }
 
 #endif  // __CUDACC__

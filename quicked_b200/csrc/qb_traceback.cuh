@@ -53,7 +53,9 @@ __device__ __forceinline__ bool cell_written(const int2 *ranges, int B, int c, i
     return w >= lo && w <= r.y;
 }
 
-// The walk of ONE leaf by one thread (see k_traceback_thread).
+// The walk of ONE leaf by one thread (see k_traceback_thread).  Tight version for narrow bands: 32-bit cell keys,
+// ONE emit point per step (the three outcomes D / I / diagonal are selected, not branched, so divergent lanes do not
+// serialise three copies of the op writer), and the live range of the current column block cached in registers.
 __device__ __forceinline__ void traceback_walk_thread(int m, int n, i64 cutoff, const ulonglong2 *mat, i64 cs, i64 wsd,
                                                       const int2 *ranges, i64 rstride, const unsigned char *__restrict__ praw,
                                                       const unsigned char *__restrict__ traw, u32 *ops, int ops_cap, LeafOut &o)
@@ -64,12 +66,12 @@ __device__ __forceinline__ void traceback_walk_thread(int m, int n, i64 cutoff, 
     int h = n - 1, v = m - 1;
     // cached live ranges of column blocks kb_c and kb_c + 1
     int kb_c = -2; int2 rg0 = make_int2(0, -1), rg1 = make_int2(0, -1);
-    // cached entries: key = column * B + word (the reference's flat index), -1 = empty
-    i64 keyR = -1, keyL = -1;
+    // cached entries: key = column * B + word (the reference's flat index; < 2^31 for the narrow bands walked here)
+    int keyR = -1, keyL = -1;
     ulonglong2 eR = make_ulonglong2(0, 0), eL = make_ulonglong2(0, 0);
     auto fetch = [&](int c, int wd) -> ulonglong2 {
         // never-written cells read as 0 (see cell_written); the live range of column c comes from block (c-1)/64
-        if (c < 0 || c > n || wd < 0 || wd >= B) return make_ulonglong2(0, 0);
+        if ((unsigned)c > (unsigned)n || (unsigned)wd >= (unsigned)B) return make_ulonglong2(0, 0);
         if (c > 0) {
             const int kb = (c - 1) >> 6;
             if (kb != kb_c) {
@@ -88,21 +90,25 @@ __device__ __forceinline__ void traceback_walk_thread(int m, int n, i64 cutoff, 
         // word numbers with C truncation; a row outside the band's coordinates makes the reference index the flat
         // [column][word] array across column boundaries (only possible when the band is too narrow)
         const int wr = evr / 64, wl = ev / 64;
-        const i64 fR = (i64)(h + 1) * B + wr, fL = (i64)h * B + wl;
+        const int fR = (h + 1) * B + wr, fL = h * B + wl;
         if (fR != keyR) {
             if (fR == keyL) eR = eL;
-            else if (wr >= 0 && wr < B) eR = fetch(h + 1, wr);
-            else eR = fR >= 0 ? fetch((int)(fR / B), (int)(fR % B)) : make_ulonglong2(0, 0);
+            else if ((unsigned)wr < (unsigned)B) eR = fetch(h + 1, wr);
+            else eR = fR >= 0 ? fetch(fR / B, fR % B) : make_ulonglong2(0, 0);
             keyR = fR;
         }
         if (fL != keyL) {
-            if (wl >= 0 && wl < B) eL = fetch(h, wl);
-            else eL = fL >= 0 ? fetch((int)(fL / B), (int)(fL % B)) : make_ulonglong2(0, 0);
+            if ((unsigned)wl < (unsigned)B) eL = fetch(h, wl);
+            else eL = fL >= 0 ? fetch(fL / B, fL % B) : make_ulonglong2(0, 0);
             keyL = fL;
         }
-        if ((eR.x >> (evr & 63)) & 1ull) { w.emit(OP_D); --v; }
-        else if ((eL.y >> (ev & 63)) & 1ull) { w.emit(OP_I); --h; }
-        else { w.emit(traw[h] == praw[v] ? OP_M : OP_X); --h; --v; }
+        const bool isD = (eR.x >> (evr & 63)) & 1ull;
+        const bool isI = (eL.y >> (ev & 63)) & 1ull;
+        int op = isD ? OP_D : OP_I;
+        if (!isD && !isI) op = (traw[h] == praw[v]) ? OP_M : OP_X;     // RAW byte compare (bpm_banded.c:1012)
+        w.emit(op);
+        v -= (isD || !isI) ? 1 : 0;          // D and diagonal consume a pattern row
+        h -= isD ? 0 : 1;                    // I and diagonal consume a text column
     }
     while (h >= 0) { w.emit(OP_I); --h; }
     while (v >= 0) { w.emit(OP_D); --v; }

@@ -1315,18 +1315,21 @@ int qb200_measure_int_peak(qb200_ctx_t *ctx, double *tera_ops_per_s)
 }
 
 // Pipelined host-in / host-out path: the batch is cut into sub-batches of about one resident wave of the WindowEd
-// kernel; four worker contexts (own stream, own pools, own host thread) take sub-batches round-robin, so the H2D copy
-// of one overlaps the kernels and the D2H copies of the others and the PCIe link stays busy.  CIGAR strings stay packed in input order: a worker waits for the text
-// totals of the preceding sub-batches (known right after their run) before it downloads into the caller's buffer.
+// kernel and pushed through a 3-stage software pipeline over a ring of worker contexts (own stream, own pools):
+//   uploader thread  : host prep + H2D of sub-batch k      (PCIe host->device busy back to back)
+//   compute thread   : kernels of sub-batch k-1            (the GPU runs one sub-batch at a time, at full occupancy)
+//   downloader thread: D2H of sub-batch k-2 into the caller's buffers (PCIe device->host, full duplex with the upload)
+// CIGAR strings stay packed in input order: the compute thread knows the text bytes of every earlier sub-batch.
 static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res)
 {
     const i64 n = b->n_pairs;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const i64 sub = (i64)sms * kWsCtasPerSm * kWsThreads;
+    i64 sub = (i64)sms * kWsResidentCtas * kWsThreads * 2;
+    if (const char *e = getenv("QB200_SUB_PAIRS")) sub = std::max<i64>(1024, atoll(e));
     const int S = (int)((n + sub - 1) / sub);
-    int NW = 3;
-    if (const char *e = getenv("QB200_WORKERS")) NW = std::max(1, std::min(atoi(e), (int)qb200_ctx::kWorkers));
+    int NW = 3;                                               // ring slots
+    if (const char *e = getenv("QB200_WORKERS")) NW = std::max(2, std::min(atoi(e), (int)qb200_ctx::kWorkers));
     const bool trace = getenv("QB200_TRACE") != nullptr;
     for (int k = 0; k < NW; ++k) {
         if (!ctx->child[k]) {
@@ -1337,101 +1340,116 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
     }
     std::mutex mu;
     std::condition_variable cv;
-    std::vector<i64> text_total((size_t)S, -1);        // bytes of CIGAR text of each sub-batch, -1 = not known yet
-    std::vector<int> rcs(NW, 0);
-    std::vector<qb200_stats_t> acc(NW);
-    memset(acc.data(), 0, sizeof(qb200_stats_t) * NW);
+    int uploaded = 0, computed = 0, downloaded = 0;          // sub-batches that finished each stage
+    int failed = 0;
+    std::vector<i64> text_base((size_t)S + 1, 0);             // first CIGAR byte of each sub-batch (prefix of totals)
     const bool want_cigar = !params->only_score && res->cigar_off;
     bool capacity_short = false;
+    qb200_stats_t acc;
+    memset(&acc, 0, sizeof acc);
+    auto t_ms = [](std::chrono::steady_clock::time_point x) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - x).count(); };
 
-    auto worker = [&](int wid) {
-        qb200_ctx *c = ctx->child[wid];
-        cudaSetDevice(c->device);
-        for (int sidx = wid; sidx < S; sidx += NW) {
-            const i64 i0 = (i64)sidx * sub, i1 = std::min(n, i0 + sub), cnt = i1 - i0;
-            int rc = 0;
-            // byte range of this sub-batch in the caller's packed buffer
-            i64 lo = b->seqs_bytes, hi = 0;
+    auto fail = [&](int rc, qb200_ctx *c) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed) { failed = rc; ctx->err = c->err; }
+        cv.notify_all();
+    };
+
+    std::thread uploader([&] {
+        cudaSetDevice(ctx->device);
+        std::vector<int64_t> po, to;
+        for (int k = 0; k < S; ++k) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || k < downloaded + NW; });        // ring slot k % NW is free again
+                if (failed) return;
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            qb200_ctx *c = ctx->child[k % NW];
+            const i64 i0 = (i64)k * sub, i1 = std::min(n, i0 + sub), cnt = i1 - i0;
+            i64 lo = b->seqs_bytes, hi = 0;                   // byte range of this sub-batch in the caller's packed buffer
             for (i64 i = i0; i < i1; ++i) {
                 lo = std::min<i64>(lo, std::min<i64>(b->pattern_off[i], b->text_off[i]));
                 hi = std::max<i64>(hi, std::max<i64>(b->pattern_off[i] + b->pattern_len[i], b->text_off[i] + b->text_len[i]));
             }
             if (hi < lo) { lo = 0; hi = 0; }
-            std::vector<int64_t> po((size_t)cnt), to((size_t)cnt);
+            po.resize((size_t)cnt); to.resize((size_t)cnt);
             for (i64 i = 0; i < cnt; ++i) { po[(size_t)i] = b->pattern_off[i0 + i] - lo; to[(size_t)i] = b->text_off[i0 + i] - lo; }
             qb200_batch_t sb = {b->seqs + lo, hi - lo, cnt, po.data(), b->pattern_len + i0, to.data(), b->text_len + i0};
-            const auto t_a = std::chrono::steady_clock::now();
-            rc = qb200_upload(c, &sb);
-            const auto t_b = std::chrono::steady_clock::now();
-            if (!rc) rc = qb200_run(c, params);
-            const auto t_c = std::chrono::steady_clock::now();
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                text_total[(size_t)sidx] = rc ? 0 : (want_cigar && c->have_cigar ? c->cigar_total : 0);
-                if (rc && !rcs[wid]) { rcs[wid] = rc; ctx->err = c->err; }
-            }
+            const int rc = qb200_upload(c, &sb);
+            if (rc) { fail(rc, c); return; }
+            if (trace) fprintf(stderr, "[qb200 pipeline] sub %d uploaded in %.2f ms\n", k, t_ms(t0));
+            { std::lock_guard<std::mutex> lk(mu); uploaded = k + 1; }
             cv.notify_all();
-            if (rc) continue;
-            // where do this sub-batch's strings start?  wait for the totals of all earlier sub-batches
-            i64 base = 0;
+        }
+    });
+    std::thread computer([&] {
+        cudaSetDevice(ctx->device);
+        for (int k = 0; k < S; ++k) {
             {
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { for (int q = 0; q < sidx; ++q) if (text_total[(size_t)q] < 0) return false; return true; });
-                for (int q = 0; q < sidx; ++q) base += text_total[(size_t)q];
+                cv.wait(lk, [&] { return failed || k < uploaded; });
+                if (failed) return;
             }
-            std::vector<int64_t> loc_off;
+            const auto t0 = std::chrono::steady_clock::now();
+            qb200_ctx *c = ctx->child[k % NW];
+            const int rc = qb200_run(c, params);
+            if (rc) { fail(rc, c); return; }
+            if (trace) fprintf(stderr, "[qb200 pipeline] sub %d computed in %.2f ms (gpu %.2f: prep %.2f ws %.2f fused %.2f fill %.2f trace %.2f cigar %.2f)\n", k, t_ms(t0), c->stats.ms_total,
+                               c->stats.ms_prepare, c->stats.ms_windowed_s, c->stats.ms_fused, c->stats.ms_align_fill, c->stats.ms_align_trace, c->stats.ms_cigar);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                text_base[(size_t)k + 1] = text_base[(size_t)k] + ((want_cigar && c->have_cigar) ? c->cigar_total : 0);
+                computed = k + 1;
+            }
+            cv.notify_all();
+        }
+    });
+    std::thread downloader([&] {
+        cudaSetDevice(ctx->device);
+        std::vector<int64_t> loc_off;
+        for (int k = 0; k < S; ++k) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || k < computed; });
+                if (failed) return;
+            }
+            const auto t0 = std::chrono::steady_clock::now();
+            qb200_ctx *c = ctx->child[k % NW];
+            const i64 i0 = (i64)k * sub, i1 = std::min(n, i0 + sub), cnt = i1 - i0;
+            const i64 base = text_base[(size_t)k], need = text_base[(size_t)k + 1] - base;
             if (res->cigar_off) loc_off.resize((size_t)cnt + 1);
             qb200_results_t sr;
             sr.score = res->score ? res->score + i0 : nullptr;
             sr.status = res->status ? res->status + i0 : nullptr;
             sr.cigar_off = res->cigar_off ? loc_off.data() : nullptr;
-            const i64 need = text_total[(size_t)sidx];
             const bool fits = want_cigar && res->cigar && base + need <= res->cigar_capacity;
             sr.cigar = fits ? res->cigar + base : nullptr;
             sr.cigar_capacity = fits ? res->cigar_capacity - base : 0;
             sr.cigar_bytes = 0;
-            rc = qb200_download(c, &sr);
-            if (rc == QB200_ERR_CAPACITY) { std::lock_guard<std::mutex> lk(mu); capacity_short = true; rc = 0; }
-            if (trace) {
-                const auto t_d = std::chrono::steady_clock::now();
-                auto ms = [](std::chrono::steady_clock::time_point x, std::chrono::steady_clock::time_point y) { return std::chrono::duration<double, std::milli>(y - x).count(); };
-                fprintf(stderr, "[qb200 pipeline] worker %d sub %d: upload %.2f ms, run %.2f ms (gpu %.2f), download %.2f ms\n", wid, sidx, ms(t_a, t_b), ms(t_b, t_c), c->stats.ms_total, ms(t_c, t_d));
-            }
+            int rc = qb200_download(c, &sr);
+            if (rc == QB200_ERR_CAPACITY) { capacity_short = true; rc = 0; }
+            if (rc) { fail(rc, c); return; }
             if (res->cigar_off) for (i64 i = 0; i < cnt; ++i) res->cigar_off[i0 + i] = (want_cigar ? loc_off[(size_t)i] + base : 0);   // local -> global
-            if (rc && !rcs[wid]) { std::lock_guard<std::mutex> lk(mu); rcs[wid] = rc; ctx->err = c->err; }
             const qb200_stats_t &st = c->stats;
-            qb200_stats_t &a = acc[(size_t)wid];
-            a.n_pairs += st.n_pairs; a.kernel_launches += st.kernel_launches; a.word_steps += st.word_steps;
-            a.word_steps_windowed += st.word_steps_windowed; a.word_steps_banded += st.word_steps_banded; a.cells += st.cells;
-            a.h2d_bytes += st.h2d_bytes; a.d2h_bytes += st.d2h_bytes; a.pairs_stage2 += st.pairs_stage2; a.pairs_stage3 += st.pairs_stage3;
-            a.banded_tries += st.banded_tries; a.hirschberg_splits += st.hirschberg_splits; a.leaves += st.leaves;
-            a.ms_total += st.ms_total; a.ms_prepare += st.ms_prepare; a.ms_windowed_s += st.ms_windowed_s; a.ms_windowed_l += st.ms_windowed_l;
-            a.ms_banded += st.ms_banded; a.ms_align_fill += st.ms_align_fill; a.ms_align_trace += st.ms_align_trace; a.ms_cigar += st.ms_cigar;
-            a.matrix_bytes += st.matrix_bytes; a.ms_fused += st.ms_fused; a.pairs_fused += st.pairs_fused;
+            acc.n_pairs += st.n_pairs; acc.kernel_launches += st.kernel_launches; acc.word_steps += st.word_steps;
+            acc.word_steps_windowed += st.word_steps_windowed; acc.word_steps_banded += st.word_steps_banded; acc.cells += st.cells;
+            acc.h2d_bytes += st.h2d_bytes; acc.d2h_bytes += st.d2h_bytes; acc.pairs_stage2 += st.pairs_stage2; acc.pairs_stage3 += st.pairs_stage3;
+            acc.banded_tries += st.banded_tries; acc.hirschberg_splits += st.hirschberg_splits; acc.leaves += st.leaves;
+            acc.ms_total += st.ms_total; acc.ms_prepare += st.ms_prepare; acc.ms_windowed_s += st.ms_windowed_s; acc.ms_windowed_l += st.ms_windowed_l;
+            acc.ms_banded += st.ms_banded; acc.ms_align_fill += st.ms_align_fill; acc.ms_align_trace += st.ms_align_trace; acc.ms_cigar += st.ms_cigar;
+            acc.matrix_bytes += st.matrix_bytes; acc.ms_fused += st.ms_fused; acc.pairs_fused += st.pairs_fused;
+            if (trace) fprintf(stderr, "[qb200 pipeline] sub %d downloaded in %.2f ms\n", k, t_ms(t0));
+            { std::lock_guard<std::mutex> lk(mu); downloaded = k + 1; }
+            cv.notify_all();
         }
-    };
-    {
-        std::vector<std::thread> th;
-        for (int k = 0; k < NW; ++k) th.emplace_back(worker, k);
-        for (auto &t : th) t.join();
-    }
-    for (int k = 0; k < NW; ++k) if (rcs[k]) return rcs[k];
-    i64 total = 0;
-    for (int q = 0; q < S; ++q) total += std::max<i64>(text_total[(size_t)q], 0);
+    });
+    uploader.join(); computer.join(); downloader.join();
+    if (failed) return failed;
+    const i64 total = text_base[(size_t)S];
     if (res->cigar_off) res->cigar_off[n] = want_cigar ? total : 0;
     res->cigar_bytes = want_cigar ? total : 0;
-    qb200_stats_t &o = ctx->stats;
-    memset(&o, 0, sizeof o);
-    for (int w = 0; w < NW; ++w) {
-        const qb200_stats_t &a = acc[(size_t)w];
-        o.n_pairs += a.n_pairs; o.kernel_launches += a.kernel_launches; o.word_steps += a.word_steps;
-        o.word_steps_windowed += a.word_steps_windowed; o.word_steps_banded += a.word_steps_banded; o.cells += a.cells;
-        o.h2d_bytes += a.h2d_bytes; o.d2h_bytes += a.d2h_bytes; o.pairs_stage2 += a.pairs_stage2; o.pairs_stage3 += a.pairs_stage3;
-        o.banded_tries += a.banded_tries; o.hirschberg_splits += a.hirschberg_splits; o.leaves += a.leaves;
-        o.ms_total += a.ms_total; o.ms_prepare += a.ms_prepare; o.ms_windowed_s += a.ms_windowed_s; o.ms_windowed_l += a.ms_windowed_l;
-        o.ms_banded += a.ms_banded; o.ms_align_fill += a.ms_align_fill; o.ms_align_trace += a.ms_align_trace; o.ms_cigar += a.ms_cigar;
-        o.matrix_bytes += a.matrix_bytes; o.ms_fused += a.ms_fused; o.pairs_fused += a.pairs_fused;
-    }
+    ctx->stats = acc;
     ctx->ran = false;       // results live in the caller's buffers, not in this context
     return capacity_short ? QB200_ERR_CAPACITY : 0;
 }

@@ -33,7 +33,24 @@ WORKLOADS = {   # name: (length, error, pairs per GPU, description)
     "c2": (1000, 0.10, 1000000, "generate_dataset 1 kbp pairs at 10% error, 1M pairs, QuickEd score + CIGAR"),
     "c3": (10000, 0.20, 100000, "generate_dataset 10 kbp pairs at 20% error, 100k pairs, score + CIGAR"),
     "c4": (100000, 0.20, 2048, "generate_dataset 100 kbp pairs at 20% error, 2048 pairs, Hirschberg CIGAR"),
+    "c5": (0, 0.0, 200000, "mixed lengths 100 bp..100 kbp (equal bases per class), errors 5..25 %, length-bucketed, work-balanced ranges"),
 }
+C5_LENGTHS = [100, 300, 1000, 3000, 10000, 30000, 100000]
+C5_ERRORS = [0.05, 0.10, 0.15, 0.20, 0.25]
+
+
+def generate_c5(base_pairs, seed):
+    """BASELINE config 5: one packed batch, classes in order of increasing length (length-bucketed), equal bases per
+    class (pairs per class = base_pairs * 100 / L), error rate cycling 5..25 % inside every class."""
+    import quicked_b200 as qb
+    bufs, po, pl, to, tl, off = [], [], [], [], [], 0
+    for ci, L in enumerate(C5_LENGTHS):
+        per_err = max(1, base_pairs * 100 // L // len(C5_ERRORS))
+        for ei, e in enumerate(C5_ERRORS):
+            s_, po_, pl_, to_, tl_ = qb.generate_pairs_native(seed * 1000 + ci * 10 + ei, per_err, L, e)
+            bufs.append(s_); po.append(po_ + off); to.append(to_ + off); pl.append(pl_); tl.append(tl_)
+            off += s_.size
+    return np.concatenate(bufs), np.concatenate(po), np.concatenate(pl), np.concatenate(to), np.concatenate(tl)
 ALGOS = {"quicked": 0, "windowed": 1, "banded": 2, "hirschberg": 3}
 
 
@@ -151,6 +168,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        if args.workload == "c5":
+            raise SystemExit("--impl reference is defined for the uniform workloads c1..c4")
         # ~600 us/pair-thread at 10 kbp, ~50 us at 1 kbp, ~6 us at 100 bp: size each step for a few seconds
         per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000}[args.workload]
         cores = os.cpu_count() or 1
@@ -196,8 +215,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # rank r aligns the contiguous index range [r*n_pairs, (r+1)*n_pairs) of the (virtual) job
-    seqs, po, pl, to, tl = qb.generate_pairs_native(1000 + rank, n_pairs, length, error)
+    scaling = "weak"
+    if args.workload == "c5":
+        # strong scaling: ONE mixed job, length-bucketed, cut into contiguous work-balanced ranges (no collective)
+        from quicked_b200.sharding import balanced_ranges
+        seqs, po, pl, to, tl = generate_c5(n_pairs, 77)
+        lo, hi = balanced_ranges(list(zip(pl.tolist(), tl.tolist())), world)[rank]
+        b0 = int(min(po[lo], to[lo])) & ~15
+        b1 = int(max(po[hi - 1] + pl[hi - 1], to[hi - 1] + tl[hi - 1]))
+        seqs = np.ascontiguousarray(np.concatenate([seqs[b0:b1], np.zeros((-(b1 - b0)) % 16 + 16, np.uint8)]))
+        po, to, pl, tl = po[lo:hi] - b0, to[lo:hi] - b0, np.ascontiguousarray(pl[lo:hi]), np.ascontiguousarray(tl[lo:hi])
+        config["job_pairs"] = int(sum(max(1, n_pairs * 100 // L // len(C5_ERRORS)) * len(C5_ERRORS) for L in C5_LENGTHS))
+        config["rank0_pairs"] = int(hi - lo)
+        length = int(np.sqrt(float(np.mean(pl.astype(np.float64) * tl))))     # for the GCUPS_equiv line only
+        n_pairs = int(hi - lo)
+        scaling = "strong"
+    else:
+        # rank r aligns the contiguous index range [r*n_pairs, (r+1)*n_pairs) of the (virtual) job
+        seqs, po, pl, to, tl = qb.generate_pairs_native(1000 + rank, n_pairs, length, error)
     lib = qb.load()
     # pinned host staging for the end-to-end leg
     import ctypes as C
@@ -233,7 +268,14 @@ def main():
     clocks = sampler.stop()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
-    value = world * n_pairs / (ms_step * 1e-3)
+    total_pairs = world * n_pairs
+    if scaling == "strong" and world > 1:
+        tp = torch.tensor([float(n_pairs)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tp)
+        total_pairs = int(tp.item())
+    elif scaling == "strong":
+        total_pairs = n_pairs
+    value = total_pairs / (ms_step * 1e-3)
     st = gpu.stats()
     status, score, off, cig = gpu.download()
     ok_frac = float((status >= 0).mean())
@@ -258,7 +300,7 @@ def main():
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * n_pairs * args.steps / dt
+    e2e_value = total_pairs * args.steps / dt
     st_e = gpu.stats()
     assert np.array_equal(score_h, score), "end-to-end scores differ from the resident run"
 
@@ -283,8 +325,8 @@ def main():
                 "peak_source": "qb200_measure_int_peak (LOP3+IADD3 microbenchmark, this run)"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000}[args.workload]
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "c5":
+        per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000, "c5": 50}[args.workload]
         cores = os.cpu_count() or 1
         sample = args.cpu_sample or int(max(cores, min(n_pairs, 15e6 * cores / per_pair_us)))
         v, used, kind, cdt = cpu_reference_arm(length, error, algo_kw, sample, seed=1000)
@@ -293,7 +335,7 @@ def main():
 
     if rank == 0:
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64",
                "data": "synthetic", "config": config,
                "gcups_equiv": value * length * length / 1e9,
                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(st_e["h2d_bytes"]),

@@ -39,3 +39,30 @@ def align_sharded(pairs, rank, world, device=None, **params):
     if rank != 0:
         return None
     return [(s[0], s[1], c) for s, c in zip(sc, cg)]
+
+
+def estimated_work(m, n, error=0.15):
+    """Rough word-step count of QUICKED for one pair: WindowEd(S) (2 words x 2 passes over the text) plus a band of
+    ceil(error * max(m, n) / 64) + 2 blocks over n columns (twice when Hirschberg splits).  Only the relative values
+    matter: it is the key for balancing mixed-length batches across GPUs (BASELINE config 5)."""
+    L = max(m, n)
+    band = -(-int(error * L) // 64) + 2
+    split = 2 if band * n * 16 > (1 << 24) else 1
+    return 4 * n + band * n * split
+
+
+def balanced_ranges(lengths, world, error=0.15):
+    """Contiguous index ranges [lo, hi) per rank with approximately equal estimated work (prefix-sum split).
+    `lengths` = [(m, n), ...] in input order; contiguous ranges keep the host-side gather a plain concatenation."""
+    work = [estimated_work(m, n, error) for m, n in lengths]
+    total = float(sum(work)) or 1.0
+    bounds, acc, nxt = [0], 0.0, 1
+    for i, w in enumerate(work):
+        acc += w
+        while nxt < world and acc >= total * nxt / world:
+            bounds.append(i + 1)
+            nxt += 1
+    while len(bounds) < world:
+        bounds.append(len(work))
+    bounds.append(len(work))
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]

@@ -48,3 +48,21 @@ def test_world_size_2_gloo(tmp_path):
                         "--master-port", "29517", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "OK 1001" in r.stdout
+
+
+def test_balanced_ranges_mixed_lengths():
+    """BASELINE config 5: lengths 100 bp .. 100 kbp, equal bases per class; ranges must tile the batch and balance work"""
+    import random
+    from quicked_b200.sharding import balanced_ranges, estimated_work
+    rnd = random.Random(3)
+    lengths = []
+    for L, cnt in [(100, 10000), (300, 3333), (1000, 1000), (3000, 333), (10000, 100), (30000, 33), (100000, 10)]:
+        lengths += [(L, L)] * cnt
+    rnd.shuffle(lengths)
+    for world in (1, 2, 4, 8):
+        spans = balanced_ranges(lengths, world)
+        assert spans[0][0] == 0 and spans[-1][1] == len(lengths)
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        loads = [sum(estimated_work(m, n) for m, n in lengths[lo:hi]) for lo, hi in spans]
+        biggest = max(estimated_work(m, n) for m, n in lengths)      # a contiguous split cannot beat one pair's granularity
+        assert max(loads) <= sum(loads) / world + biggest, (world, loads)

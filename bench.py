@@ -54,6 +54,24 @@ def generate_c5(base_pairs, seed):
 ALGOS = {"quicked": 0, "windowed": 1, "banded": 2, "hirschberg": 3}
 
 
+def ncu_traffic_bytes(kernel_substr, csv_name="r1_ncu_full_c2_v3_raw.csv"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel_substr`, from the committed `ncu --set full`
+    capture of this same command (profiles/, 1 M pairs of configs[1]); None when the capture is not there."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        for r in rows[2:]:
+            if kernel_substr in r[ik]:
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    except Exception:
+        return None
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -316,7 +334,9 @@ def main():
     if fill_ms > 0:
         ach = fill_bytes / (fill_ms * 1e-3) / 1e9
         roof = {"kernel": "k_banded_thread/k_banded_warp (BandEd full-matrix fill)", "bound": "hbm", "achieved": ach,
-                "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": ach / peaks.get("hbm_gbs"), "traffic": None,
+                "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": ach / peaks.get("hbm_gbs"),
+                "traffic": ncu_traffic_bytes("k_banded_thread") if (args.workload == "c2" and n_pairs == 1000000 and args.algo == "quicked") else None,
+                "algorithmic_bytes": fill_bytes,
                 "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs", "algorithmic_bytes_per_word_step": 16,
                 "ms_per_launch": fill_ms}
     int_roof = {"achieved_tops": 24.0 * st["word_steps"] / (ms_step * 1e-3) / 1e12, "peak_tops": int_peak,

@@ -271,3 +271,54 @@ def test_fused_and_planned_paths_agree(oracle, fused, monkeypatch):
         for (p, t), g in zip(pairs, got):
             assert g == oracle.align(p, t, algo=0, force_scalar=fs)
     a.close()
+
+
+def test_edge_cases_match_oracle(gpu, oracle):
+    """empty batch, single characters, identical / unrelated sequences, all-N, very unequal lengths, lowercase"""
+    assert gpu.align([]) == []
+    rng = np.random.default_rng(99)
+    rnd = lambda k: bytes(rng.choice(list(b"ACGT"), size=k).astype(np.uint8))
+    s500 = rnd(500)
+    pairs = [("A", "A"), ("A", "C"), ("A", "ACGTACGT"), ("ACGTACGT", "A"), (s500, s500), (s500, rnd(500)), ("N" * 200, "N" * 190),
+             ("N" * 100, rnd(100)), (s500.lower(), s500), (rnd(1), rnd(500)), (rnd(500), rnd(1)), (rnd(64), rnd(64)), (rnd(65), rnd(63)),
+             (rnd(128), rnd(128)), (rnd(127), rnd(129)), (rnd(4096), rnd(4096)), ("ACGT" * 300, "ACGT" * 299 + "ACG"), (rnd(700), rnd(100)),
+             (rnd(100), rnd(700)), ("", "A"), ("A", "")]
+    for algo in (0, 1, 2, 3):
+        for fs in (False, True):
+            got = gpu.align(pairs, algo=algo, force_scalar=fs, bandwidth=25)
+            for (p, t), g in zip(pairs, got):
+                p = p.decode() if isinstance(p, bytes) else p
+                t = t.decode() if isinstance(t, bytes) else t
+                exp = oracle.align(p, t, algo=algo, force_scalar=fs, bandwidth=25)
+                assert g == exp, (algo, fs, len(p), len(t), g[:2], exp[:2])
+                if g[2]:
+                    assert replay(expand_rle(g[2]), p, t) == g[1]
+
+
+def test_large_batch_properties(gpu):
+    """full-size style checks that do not need the oracle: scores bounded by the planted edits, CIGARs replay,
+    identical pairs give the same answer wherever they sit in the batch (no cross-pair interference)"""
+    import quicked_b200 as qb
+    n = 60000
+    seqs, po, pl, to, tl = qb.generate_pairs_native(3, n, 1000, 0.10)
+    # plant duplicates of pair 0 at far-apart positions
+    raw = seqs.tobytes()
+    gpu.upload_arrays(seqs, po, pl, to, tl)
+    gpu.run(algo=0)
+    status, score, off, cig = gpu.download()
+    assert (status == 1).all()
+    assert (score <= 100).all() and (score >= 0).all()          # 100 planted edits are an upper bound of the distance
+    text = cig.tobytes()
+    for i in list(range(0, n, 997)) + [n - 1]:
+        c = text[off[i]:off[i + 1] - 1].decode()
+        assert replay(expand_rle(c), raw[po[i]:po[i] + pl[i]].decode(), raw[to[i]:to[i] + tl[i]].decode()) == score[i]
+    # the same pairs in reverse order must give the same results
+    idx = np.arange(n)[::-1].copy()
+    gpu.upload_arrays(seqs, po[idx].copy(), pl[idx].copy(), to[idx].copy(), tl[idx].copy())
+    gpu.run(algo=0)
+    status2, score2, off2, cig2 = gpu.download()
+    assert np.array_equal(score2, score[idx])
+    t2 = cig2.tobytes()
+    for i in range(0, n, 4999):
+        j = n - 1 - i
+        assert t2[off2[i]:off2[i + 1]] == text[off[j]:off[j + 1]]

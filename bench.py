@@ -128,29 +128,16 @@ class ClockSampler:
 
 
 def cpu_reference_arm(length, error, algo_kw, sample_pairs, seed, threads=None):
-    """Time the reference's CPU implementation (oracle/_ref when built, else the oracle port) on `sample_pairs`
-    pairs of the workload with all host threads.  -> (pairs/s, cores, kind, seconds)"""
-    from concurrent.futures import ThreadPoolExecutor
+    """Time the reference's CPU implementation on `sample_pairs` pairs of the workload with all host threads: ONE native
+    call (oracle/_ref/libref_batch.so = the unmodified reference driven like its own align_benchmark does per thread;
+    else the oracle port), so no Python overhead lands in the timed region.  -> (pairs/s, threads, kind, seconds)"""
     from oracle import harness
     import quicked_b200 as qb
     seqs, po, pl, to, tl = qb.generate_pairs_native(seed, sample_pairs, length, error)
-    raw = seqs.tobytes()
-    pairs = [(raw[po[i]:po[i] + pl[i]], raw[to[i]:to[i] + tl[i]]) for i in range(sample_pairs)]
-    kind = "reference" if harness.Reference.available() else "port"
-    threads = threads or os.cpu_count() or 1
-    threads = max(1, min(threads, sample_pairs))
-
-    def work(chunk):
-        impl = harness.Reference() if kind == "reference" else harness.Oracle()   # one handle per thread (ctypes releases the GIL)
-        s = 0
-        for p, t in chunk:
-            s += impl.align(p, t, **algo_kw)[1]
-        return s
-
-    chunks = [pairs[i::threads] for i in range(threads)]
+    threads = max(1, min(threads or os.cpu_count() or 1, sample_pairs))
+    harness.cpu_batch_align(seqs, po[:threads], pl[:threads], to[:threads], tl[:threads], threads, **algo_kw)   # warm the libraries
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(work, chunks))
+    kind, _, _ = harness.cpu_batch_align(seqs, po, pl, to, tl, threads, **algo_kw)
     dt = time.perf_counter() - t0
     return sample_pairs / dt, threads, kind, dt
 

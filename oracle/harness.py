@@ -13,6 +13,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libqoracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libquicked_ref.so")
+REF_BATCH_SO = os.path.join(HERE, "_ref", "libref_batch.so")
 
 QUICKED, WINDOWED, BANDED, HIRSCHBERG = 0, 1, 2, 3
 
@@ -175,3 +176,28 @@ class Reference:
 
     def status_msg(self, st):
         return self.lib.quicked_status_msg(st).decode()
+
+
+def cpu_batch_align(seqs, po, pl, to, tl, threads, algo=0, bandwidth=15, window_size=9, overlap_size=1, only_score=False,
+                    force_scalar=False, want_scores=False):
+    """Time-critical CPU baseline: ONE native call aligns the whole packed batch on `threads` pthreads, through the
+    unmodified reference (oracle/_ref/libref_batch.so, the per-thread loop of the reference's align_benchmark) when it is
+    built, else through the oracle port.  numpy arrays in the layout of qb200_batch_t.  -> (kind, cigar_bytes, scores|None)"""
+    import numpy as np
+    n = int(po.size)
+    scores = np.zeros(n, np.int32) if want_scores else None
+    sp = scores.ctypes.data if want_scores else None
+    if os.path.exists(REF_BATCH_SO):
+        L = C.CDLL(REF_BATCH_SO)
+        L.ref_batch_align.restype = C.c_int64
+        L.ref_batch_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint,
+                                      C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_void_p]
+        b = L.ref_batch_align(seqs.ctypes.data, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data, n, int(threads), int(algo),
+                              int(bandwidth), int(window_size), int(overlap_size), int(only_score), int(force_scalar), sp)
+        return "reference", int(b), scores
+    o = Oracle()
+    o.lib.qo_batch_align.restype = C.c_int64
+    o.lib.qo_batch_align.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(QoParams), C.c_void_p]
+    p = o.params(algo=algo, bandwidth=bandwidth, window_size=window_size, overlap_size=overlap_size, only_score=only_score, force_scalar=force_scalar)
+    b = o.lib.qo_batch_align(seqs.ctypes.data, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data, n, int(threads), C.byref(p), sp)
+    return "port", int(b), scores

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 
 #define W64 64
 #define ALPHA 5
@@ -21,9 +22,9 @@
 #define MINI(a, b) ((a) <= (b) ? (a) : (b))
 #define ABSI(a) ((a) >= 0 ? (a) : -(a))
 
-static uint64_t g_ws_windowed, g_ws_banded;
-static int g_splits;
-static int g_ref_undefined;   /* set when the reference would read uninitialised memory (see banded_score_run) */
+static __thread uint64_t g_ws_windowed, g_ws_banded;     /* per thread: qo_batch_align runs qo_align concurrently */
+static __thread int g_splits;
+static __thread int g_ref_undefined;   /* set when the reference would read uninitialised memory (see banded_score_run) */
 
 uint64_t qo_word_steps_total(void) { return g_ws_windowed + g_ws_banded; }
 
@@ -706,3 +707,43 @@ char *qo_align_ops(const qo_params_t *prm, const char *pattern, int m, const cha
 }
 
 void qo_free_result(qo_result_t *r) { free(r->cigar); r->cigar = NULL; }
+
+/* ------------------------------------------------------------------------------------------------
+ * Native batch driver (bench.py cpu_baseline kind "port"): contiguous ranges over `threads` pthreads,
+ * like the reference tool's OpenMP loop (tools/align_benchmark/align_benchmark.c:269-284).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const char *seqs; const int64_t *po, *to; const int32_t *pl, *tl; int64_t lo, hi;
+    qo_params_t prm; int32_t *score; int64_t bytes;
+} qo_job_t;
+
+static void *qo_batch_worker(void *arg)
+{
+    qo_job_t *j = (qo_job_t *)arg;
+    for (int64_t i = j->lo; i < j->hi; ++i) {
+        qo_result_t r;
+        qo_align(&j->prm, j->seqs + j->po[i], j->pl[i], j->seqs + j->to[i], j->tl[i], &r);
+        if (j->score) j->score[i] = (int32_t)r.score;
+        if (r.cigar) j->bytes += (int64_t)strlen(r.cigar);
+        qo_free_result(&r);
+    }
+    return NULL;
+}
+
+int64_t qo_batch_align(const char *seqs, const int64_t *po, const int32_t *pl, const int64_t *to, const int32_t *tl,
+                       int64_t n, int threads, const qo_params_t *prm, int32_t *score_out)
+{
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = (int)(n > 0 ? n : 1);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    qo_job_t *jobs = (qo_job_t *)malloc(sizeof(qo_job_t) * (size_t)threads);
+    for (int t = 0; t < threads; ++t) {
+        qo_job_t jb = {seqs, po, to, pl, tl, n * t / threads, n * (t + 1) / threads, *prm, score_out, 0};
+        jobs[t] = jb;
+        pthread_create(&th[t], NULL, qo_batch_worker, &jobs[t]);
+    }
+    int64_t total = 0;
+    for (int t = 0; t < threads; ++t) { pthread_join(th[t], NULL); total += jobs[t].bytes; }
+    free(th); free(jobs);
+    return total;
+}

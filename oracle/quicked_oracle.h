@@ -84,6 +84,10 @@ int64_t qo_windowed_score(const char *pattern, int m, const char *text, int n, i
 
 uint64_t qo_word_steps_total(void);   /* running counters (reset by qo_align) */
 
+/* Batch of pairs in the packed layout of include/quicked_b200.h over `threads` pthreads; returns the CIGAR bytes produced. */
+int64_t qo_batch_align(const char *seqs, const int64_t *po, const int32_t *pl, const int64_t *to, const int32_t *tl,
+                       int64_t n, int threads, const qo_params_t *prm, int32_t *score_out);
+
 #ifdef __cplusplus
 }
 #endif

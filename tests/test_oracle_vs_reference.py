@@ -133,3 +133,26 @@ def test_oracle_cigars_replay(oracle):
             for algo in (0, 1, 2, 3):
                 st, sc, ops = oracle.align_ops(p, t, algo=algo)
                 assert replay(ops, p.decode(), t.decode()) == sc
+
+
+def test_native_batch_drivers_agree(oracle, reference):
+    """the native batch drivers used for the CPU baseline (reference: oracle/ref_batch.c, port: qo_batch_align) return
+    the same scores as pair-by-pair calls"""
+    import numpy as np
+    from oracle import harness
+    from quicked_b200 import pack_pairs
+    pairs = generate_pairs(64, 800, 0.12, seed=5) + generate_pairs(64, 100, 0.05, seed=6)
+    seqs, po, pl, to, tl = pack_pairs(pairs)
+    kind, nbytes, scores = harness.cpu_batch_align(seqs, po, pl, to, tl, 4, algo=0, want_scores=True)
+    assert kind == "reference" and nbytes > 0
+    exp = [oracle.align(p, t)[1] for p, t in pairs]
+    assert scores.tolist() == exp
+    # the port's driver
+    import ctypes as C
+    o = harness.Oracle()
+    o.lib.qo_batch_align.restype = C.c_int64
+    sc2 = np.zeros(len(pairs), np.int32)
+    p = o.params(algo=0)
+    o.lib.qo_batch_align(C.c_void_p(seqs.ctypes.data), C.c_void_p(po.ctypes.data), C.c_void_p(pl.ctypes.data), C.c_void_p(to.ctypes.data),
+                         C.c_void_p(tl.ctypes.data), C.c_int64(len(pairs)), C.c_int(3), C.byref(p), C.c_void_p(sc2.ctypes.data))
+    assert sc2.tolist() == exp

@@ -103,7 +103,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
             ob[r] = (blk == nblk - 1 && mmod) ? mmod - 1 : 63;      // level_mask, bpm_banded.c:88-102
 #pragma unroll
             for (int c = 0; c < kAlpha; ++c)
-                s_eq[(r * kAlpha + c) * 32 + lane] = (act && blk < tk.nbp) ? pq[(i64)c * tk.nbp + blk] : 0ull;   // past the table: no match
+                s_eq[(r * kAlpha + c) * 32 + lane] = (act && blk < tk.nbp) ? pq[(i64)blk * kPeqStride + c] : 0ull;   // past the table: no match
         }
         __syncwarp();
         const int live = last - first + 1;
@@ -268,7 +268,7 @@ k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ li
             const int j = j0 + lane;
             const bool act = j <= last;
             const int blk = j + pos_v, slot = act ? blk % cap : 0;
-            const u64 eq = (act && blk < tk.nbp) ? pq[(i64)code * tk.nbp + blk] : 0ull;
+            const u64 eq = (act && blk < tk.nbp) ? pq[(i64)blk * kPeqStride + code] : 0ull;
             u64 pv = act ? s_pv[slot] : 0ull, mv = act ? s_mv[slot] : 0ull;
             const int ob = (blk == nblk - 1 && mmod) ? mmod - 1 : 63;
             const u64 a = eq & pv, s = a + pv;
@@ -369,30 +369,60 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
             if (j < B) mat[j * wsd] = make_ulonglong2(~0ull, 0ull);               // column 0
         }
         ranges[0] = make_int2(first, last);
+        // forward text: aligned 16-byte view of the codes (the flat buffer keeps >= 48 readable bytes past its end)
+        const int csh = (int)((unsigned long long)tcodes & 15ull);
+        const uint4 *cvec = reinterpret_cast<const uint4 *>(tcodes - csh);
+        uint4 ccur = make_uint4(0, 0, 0, 0), cnxt = ccur;
+        if (!rev) { ccur = __ldg(cvec); cnxt = __ldg(cvec + 1); }
+        int st_lo = 0, st_hi = -1;                       // band slots whose match masks are staged in s_eq
         for (int col0 = 0; col0 < n; col0 += 64) {
             const int nc = min(64, n - col0);
+            // match masks of the live blocks: the band moved down one block, so the staged masks move up one slot
+            // and only blocks that were not staged before are fetched (48 B = three 16-byte loads each)
+            if (col0 > 0) {
+#pragma unroll
+                for (int j = 0; j < BMAX - 1; ++j)
+#pragma unroll
+                    for (int c = 0; c < kAlpha; ++c) s_eq[(j * kAlpha + c) * T] = s_eq[((j + 1) * kAlpha + c) * T];
+                --st_lo; --st_hi;
+            }
 #pragma unroll
             for (int j = 0; j < BMAX; ++j) {
                 const int blk = j + pos_v;
-                if (j >= first && j <= last) {
-#pragma unroll
-                    for (int c = 0; c < kAlpha; ++c)
-                        s_eq[(j * kAlpha + c) * T] = (blk < nbp) ? pq[(i64)c * nbp + blk] : 0ull;
+                if (j >= first && j <= last && (j < st_lo || j > st_hi)) {
+                    ulonglong2 q0 = make_ulonglong2(0, 0), q1 = q0, q2 = q0;
+                    if (blk < nbp) {
+                        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(pq + (i64)blk * kPeqStride);
+                        q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
+                    }
+                    s_eq[(j * kAlpha + 0) * T] = q0.x; s_eq[(j * kAlpha + 1) * T] = q0.y; s_eq[(j * kAlpha + 2) * T] = q1.x;
+                    s_eq[(j * kAlpha + 3) * T] = q1.y; s_eq[(j * kAlpha + 4) * T] = q2.x;
                 }
             }
+            st_lo = (st_lo > st_hi) ? first : min(st_lo, first);
+            st_hi = max(st_hi, last);
             // band index of the last pattern block when its carry-out sits below bit 63 (level_mask, bpm_banded.c:88-102)
             const int jl = mmod ? (nblk - 1 - pos_v) : -1;
-            for (int c0 = 0; c0 < nc; c0 += 8) {
-                u32 cd[8];                                  // eight independent code loads in flight
+            for (int c0 = 0; c0 < nc; c0 += 16) {
+                // sixteen columns' codes: one aligned 16-byte load (realigned in registers), two chunks ahead in flight
+                u32 cw[4];
+                if (rev) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int col = col0 + c0 + k;
-                    cd[k] = (c0 + k < nc) ? (u32)(rev ? tcodes[n - 1 - col] : tcodes[col]) : 4u;
+                    for (int k = 0; k < 16; ++k) {
+                        const int col = col0 + c0 + k;
+                        const u32 c = (c0 + k < nc) ? (u32)tcodes[n - 1 - col] : 4u;
+                        if ((k & 3) == 0) cw[k >> 2] = c; else cw[k >> 2] |= c << (8 * (k & 3));
+                    }
+                } else {
+                    const uint4 c2 = __ldg(cvec + (((col0 + c0) >> 4) + 2));
+                    const uint4 r = realign16(ccur, cnxt, csh);
+                    cw[0] = r.x; cw[1] = r.y; cw[2] = r.z; cw[3] = r.w;
+                    ccur = cnxt; cnxt = c2;
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 16; ++k) {
                     if (c0 + k < nc) {
-                        const int code = (int)cd[k];
+                        const int code = (int)((cw[k >> 2] >> (8 * (k & 3))) & 7u);
                         ulonglong2 *dst = mat + (i64)(col0 + c0 + k + 1) * cs;
                         u32 hp = 1, hm = 0;
 #pragma unroll

@@ -22,7 +22,7 @@ constexpr u32 kFull = 0xffffffffu;
 struct PairRec {
     i64 p_off, t_off;     // offsets of pattern / text in the packed character buffer
     int m, n;             // lengths
-    i64 peq_off;          // u64 index of the forward match-mask table in the PEQ pool ([code][nbp] layout)
+    i64 peq_off;          // u64 index of the forward match-mask table in the PEQ pool ([nbp][kPeqStride] layout)
     int nbp;              // blocks in that table = ceil(m/64) + 2 (two all-zero blocks appended)
     int pad_;
     i64 ops_off;          // u32 index of this pair's 2-bit op words in the fused-path region of the op pool
@@ -35,7 +35,7 @@ struct BandTask {
     int rev;              // 1: run on the reversed sub-sequences (Hirschberg reverse pass)
     int finish;           // score-only: number of text columns to process
     i64 cutoff;           // bound handed to the band geometry
-    i64 peq_off;          // match masks of this sub-pattern ([code][nbp])
+    i64 peq_off;          // match masks of this sub-pattern ([nbp][kPeqStride])
     int nbp;
     int pair;             // owning pair index
     i64 mat_off;          // full mode: first 16-byte (Pv,Mv) entry of this task in the matrix pool
@@ -158,6 +158,23 @@ __device__ __forceinline__ void myers_step_at(u64 eq, u64 &pv, u64 &mv, u32 hp_i
     mh = (mh << 1) | (u64)hm_in;
     pv = mh | ~(xv | ph);
     mv = ph & xv;
+}
+
+// PEQ tables are stored [block][kPeqStride] (5 match masks + 1 pad word = 48 bytes per 64-row block, 16-byte aligned):
+// everything a thread needs for one block is three 16-byte loads from two DRAM sectors.
+constexpr int kPeqStride = 6;
+
+// Bytes [s, s+16) of the 32-byte concatenation a:b (a first), 0 <= s < 16: realigns a 16-byte window of codes that
+// was fetched with two aligned 16-byte loads.
+__device__ __forceinline__ uint4 realign16(const uint4 a, const uint4 b, int s)
+{
+    const bool w2 = (s & 8) != 0, w1 = (s & 4) != 0;
+    const u32 t0 = w2 ? a.z : a.x, t1 = w2 ? a.w : a.y, t2 = w2 ? b.x : a.z, t3 = w2 ? b.y : a.w, t4 = w2 ? b.z : b.x,
+              t5 = w2 ? b.w : b.y;
+    const u32 v0 = w1 ? t1 : t0, v1 = w1 ? t2 : t1, v2 = w1 ? t3 : t2, v3 = w1 ? t4 : t3, v4 = w1 ? t5 : t4;
+    const unsigned bs = (unsigned)(s & 3) * 8u;
+    return make_uint4(__funnelshift_r(v0, v1, bs), __funnelshift_r(v1, v2, bs), __funnelshift_r(v2, v3, bs),
+                      __funnelshift_r(v3, v4, bs));
 }
 
 __device__ __forceinline__ u64 funnel_r(u64 lo, u64 hi, unsigned sh)   // (hi:lo) >> sh, 0 <= sh < 64

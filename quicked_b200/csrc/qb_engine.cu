@@ -190,7 +190,7 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
             max_n = std::max(max_n, r.n);
             PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = words;
             ctx->h_peqjobs.push_back(j);
-            words += (i64)kAlpha * r.nbp;
+            words += (i64)kPeqStride * r.nbp;
             cells += (i64)r.m * r.n;
         }
     }
@@ -281,8 +281,9 @@ int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks
     if (!peq_base) peq_base = ctx->d_peq.as<u64>();
     const int T = 128;
     const size_t smem = (size_t)kThreadBandMax * kAlpha * T * 8;
-    if (const char *e = getenv("QB200_FILL_CARVE")) cudaFuncSetAttribute(k_banded_thread<kThreadBandMax>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-    k_banded_thread<kThreadBandMax><<<(n_tasks + T - 1) / T, T, smem, ctx->stream>>>(
+    auto kern = k_banded_thread<kThreadBandMax>;
+    if (const char *e = getenv("QB200_FILL_CARVE")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+    kern<<<(n_tasks + T - 1) / T, T, smem, ctx->stream>>>(
         ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(), peq_base,
         ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(), ctx->d_counters.as<u64>());
     CK(cudaGetLastError());
@@ -496,7 +497,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     {
         Span sp(ctx, ST_PREP);
         const size_t padded = ((size_t)ctx->raw_bytes + 15) / 16 * 16;
-        CK(ctx->d_codes.reserve(padded + 32));
+        CK(ctx->d_codes.reserve(padded + 64));            // thread kernels read whole aligned 16-byte chunks, up to 48 B past a text
         const i64 nvec = (i64)(padded / 16);
         if (ctx->d_raw_ext && ((uintptr_t)ctx->d_raw_ext & 15)) { ctx->err = "device character buffer must be 16-byte aligned"; return QB200_ERR_ARG; }
         if (ctx->d_raw_ext && (size_t)ctx->raw_bytes != padded) { ctx->err = "device character buffer size must be a multiple of 16"; return QB200_ERR_ARG; }
@@ -798,7 +799,7 @@ int build_tables(qb200_ctx *ctx, std::vector<PeqJob> &jobs)
 {
     if (jobs.empty()) return 0;
     i64 words = 0;
-    for (auto &j : jobs) { j.peq_off = words; words += (i64)kAlpha * ((j.m + 63) / 64 + 2); }
+    for (auto &j : jobs) { j.peq_off = words; words += (i64)kPeqStride * ((j.m + 63) / 64 + 2); }
     CK(ctx->d_peq2.reserve((size_t)words * 8 + 64));
     CK(ctx->d_jobs2.reserve(sizeof(PeqJob) * jobs.size()));
     CK(cudaMemcpyAsync(ctx->d_jobs2.p, jobs.data(), sizeof(PeqJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));

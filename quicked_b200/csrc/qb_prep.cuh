@@ -30,7 +30,7 @@ struct PeqJob {
     i64 src_off;   // first code byte of the (sub-)pattern, forward coordinates
     int m;         // (sub-)pattern length
     int rev;       // 1: table of the reversed (sub-)pattern
-    i64 peq_off;   // destination, u64 index; layout [code][nbp], nbp = ceil(m/64)+2
+    i64 peq_off;   // destination, u64 index; layout [nbp][kPeqStride], nbp = ceil(m/64)+2
 };
 
 // One warp per table.  Each iteration covers one 64-row block: two coalesced 32-byte reads of codes, five ballots
@@ -58,11 +58,11 @@ __global__ void __launch_bounds__(256) k_build_peq(const PeqJob *__restrict__ jo
                 if (half == 0) lo[c] = b; else hi[c] = b;
             }
         }
-        if (lane < kAlpha) {
-            u32 l = 0, h = 0;
+        if (lane < kPeqStride) {
+            u32 l = 0, h = 0;                    // lane 5: the pad word
 #pragma unroll
             for (int c = 0; c < kAlpha; ++c) if (lane == c) { l = lo[c]; h = hi[c]; }
-            dst[(i64)lane * nbp + blk] = ((u64)h << 32) | l;
+            dst[(i64)blk * kPeqStride + lane] = ((u64)h << 32) | l;
         }
     }
 }

@@ -22,26 +22,26 @@ constexpr int kWsCtasPerSm = 6;                 // up to 768 resident threads pe
 constexpr int kWsResidentCtas = 4;              // CTAs per SM actually launched (scratch = 16.6 KB per resident CTA-thread group)
 constexpr int kWsQuadSlots = 65 * 2;            // u64 slots per thread in the quadrant scratch ([slot][thread] layout)
 
-// Eight columns of a FULL window (2 words x 128 columns, walk quadrant = word 1 of columns 64..128), the case of all
+// Sixteen columns of a FULL window (2 words x 128 columns, walk quadrant = word 1 of columns 64..128), the case of all
 // but the first/last windows of a pair.  MODE 0: nothing is stored, 1: columns >= 63 are stored, 2: all are stored.
+// cw: the sixteen columns' codes, one per byte.
 template <bool SSE, int MODE>
-__device__ __forceinline__ void ws_full_group8(const unsigned char *__restrict__ tcp, int c0, u32 top_in, const u64 *weq,
-                                               u64 &pv0, u64 &mv0, u64 &pv1, u64 &mv1, u64 &pv1_prev, u64 &mv1_prev,
-                                               u64 *qpv, u64 *qmv, i64 nthr)
+__device__ __forceinline__ void ws_full_group16(const uint4 cw, int c0, u32 top_in, const u64 *weq,
+                                                u64 &pv0, u64 &mv0, u64 &pv1, u64 &mv1, u64 &pv1_prev, u64 &mv1_prev,
+                                                u64 *qpv, u64 *qmv, i64 nthr)
 {
     constexpr int T = kWsThreads;
-    u32 cd[8];
+    const u32 w[4] = {cw.x, cw.y, cw.z, cw.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cd[k] = (u32)tcp[k];          // eight independent loads in flight
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 16; ++k) {
         const int c = c0 + k;
+        const u32 code = (w[k >> 2] >> (8 * (k & 3))) & 7u;
         u32 hp_in0 = top_in;
-        if (SSE) hp_in0 = (c == 0) ? top_in : ((c == 1) ? 1u : (u32)((k & 1) ^ 1));   // c0 is a multiple of 8: parity(c) = parity(k)
+        if (SSE) hp_in0 = (c == 0) ? top_in : ((c == 1) ? 1u : (u32)((k & 1) ^ 1));   // c0 is a multiple of 16: parity(c) = parity(k)
         u32 hp, hm, o1, o2;
-        myers_step(weq[cd[k] * T], pv0, mv0, hp_in0, 0u, hp, hm);
+        myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
         if (SSE && c == 127) { pv1_prev = pv1; mv1_prev = mv1; }
-        myers_step(weq[(kAlpha + cd[k]) * T], pv1, mv1, hp, hm, o1, o2);
+        myers_step(weq[(kAlpha + code) * T], pv1, mv1, hp, hm, o1, o2);
         if (MODE == 2 || (MODE == 1 && c >= 63)) {
             qpv[(i64)(c - 63) * nthr] = pv1;
             qmv[(i64)(c - 63) * nthr] = mv1;
@@ -63,7 +63,6 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
             const unsigned char *tc = codes + pr.t_off;
             const unsigned char *traw = raw + pr.t_off, *praw = raw + pr.p_off;
             const u64 *pq = peq + pr.peq_off;
-            const int nbp = pr.nbp;
             while (cv >= 0 && ch >= 0) {
                 // ---- window geometry (bpm_windowed.c:219-232) ----
                 const int v0 = max(cv - 127, 0), h0 = max(ch - 127, 0);
@@ -76,10 +75,17 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                     const unsigned sh = v0 & 63;
                     const int blk0 = v0 >> 6;
                     u64 a[kAlpha], b[kAlpha], c2[kAlpha];
-#pragma unroll
-                    for (int c = 0; c < kAlpha; ++c) {
-                        a[c] = pq[(i64)c * nbp + blk0]; b[c] = pq[(i64)c * nbp + blk0 + 1];
-                        c2[c] = (words == 2) ? pq[(i64)c * nbp + blk0 + 2] : 0ull;
+                    {
+                        // three consecutive 48-byte blocks: nine 16-byte loads from five DRAM sectors
+                        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(pq + (i64)blk0 * kPeqStride);
+                        const ulonglong2 z = make_ulonglong2(0, 0);
+                        const ulonglong2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4),
+                                         q5 = __ldg(q + 5);
+                        const ulonglong2 q6 = (words == 2) ? __ldg(q + 6) : z, q7 = (words == 2) ? __ldg(q + 7) : z,
+                                         q8 = (words == 2) ? __ldg(q + 8) : z;
+                        a[0] = q0.x; a[1] = q0.y; a[2] = q1.x; a[3] = q1.y; a[4] = q2.x;
+                        b[0] = q3.x; b[1] = q3.y; b[2] = q4.x; b[3] = q4.y; b[4] = q5.x;
+                        c2[0] = q6.x; c2[1] = q6.y; c2[2] = q7.x; c2[3] = q7.y; c2[4] = q8.x;
                     }
 #pragma unroll
                     for (int c = 0; c < kAlpha; ++c) {
@@ -95,24 +101,46 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                     qmv[0] = 0;
                 }
                 const bool full = (words == 2 && cols == 128 && cv >= 127);      // => r0 == 64, cs == 64
+                // the window's codes come in as aligned 16-byte chunks (one load per 16 columns, one chunk ahead in
+                // flight) and are realigned in registers; the flat code buffer is readable 48 B past its end
+                const int csh = (int)((unsigned long long)(tc + h0) & 15ull);
+                const uint4 *cvec = reinterpret_cast<const uint4 *>(tc + h0 - csh);
+                uint4 ccur = __ldg(cvec), cnxt = __ldg(cvec + 1);
+                u32 code_last = 4;
                 if (full) {
-                    const unsigned char *tcp = tc + h0;
-                    for (int c0 = 0; c0 < 56; c0 += 8)
-                        ws_full_group8<SSE, 0>(tcp + c0, c0, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
-                    ws_full_group8<SSE, 1>(tcp + 56, 56, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
-                    for (int c0 = 64; c0 < 128; c0 += 8)
-                        ws_full_group8<SSE, 2>(tcp + c0, c0, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+#pragma unroll 1
+                    for (int g = 0; g < 3; ++g) {
+                        const uint4 c2 = __ldg(cvec + g + 2);
+                        const uint4 r = realign16(ccur, cnxt, csh);
+                        ccur = cnxt; cnxt = c2;
+                        ws_full_group16<SSE, 0>(r, g * 16, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+                    }
+                    {
+                        const uint4 c2 = __ldg(cvec + 5);
+                        const uint4 r = realign16(ccur, cnxt, csh);
+                        ccur = cnxt; cnxt = c2;
+                        ws_full_group16<SSE, 1>(r, 48, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+                    }
+#pragma unroll 1
+                    for (int g = 4; g < 8; ++g) {
+                        const uint4 c2 = __ldg(cvec + min(g + 2, 8));
+                        const uint4 r = realign16(ccur, cnxt, csh);
+                        ccur = cnxt; cnxt = c2;
+                        ws_full_group16<SSE, 2>(r, g * 16, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+                        if (g == 7) code_last = r.w >> 24;
+                    }
                 }
-                for (int c0 = full ? cols : 0; c0 < cols; c0 += 8) {
-                    // eight independent byte loads in flight instead of one dependent load per column
-                    u32 cd[8];
+                for (int c0 = full ? cols : 0; c0 < cols; c0 += 16) {
+                    const uint4 c2 = __ldg(cvec + (c0 >> 4) + 2);
+                    const uint4 r = realign16(ccur, cnxt, csh);
+                    ccur = cnxt; cnxt = c2;
+                    const u32 cw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) cd[k] = (c0 + k < cols) ? (u32)tc[h0 + c0 + k] : 4u;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                    for (int k = 0; k < 16; ++k) {
                         const int c = c0 + k;
                         if (c < cols) {
-                            const int code = (int)cd[k];
+                            const int code = (int)((cw[k >> 2] >> (8 * (k & 3))) & 7u);
+                            if (c == cols - 1) code_last = (u32)code;
                             u32 hp_in0 = top_in;
                             if (SSE && c > 0) hp_in0 = (c == 1) | ((c & 1) ^ 1);       // :348,:393,:424
                             u32 hp, hm, o1, o2;
@@ -138,7 +166,6 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                     u64 lpv = pv0, lmv = mv0;
                     u32 hpL, hmL, o1, o2;
                     myers_step(weq[code_la * T], lpv, lmv, 1u, 0u, hpL, hmL);
-                    const int code_last = tc[h0 + cols - 1];
                     pv1 = pv1_prev; mv1 = mv1_prev;
                     myers_step(weq[(kAlpha + code_last) * T], pv1, mv1, hpL, hmL, o1, o2);
                     const i64 s = (i64)(cols - cs) * nthr;
@@ -264,7 +291,7 @@ k_windowed_warp(const WinTask *__restrict__ tasks, int n_tasks, const unsigned c
 #pragma unroll
             for (int c = 0; c < kAlpha; ++c) {
                 u64 e = 0;
-                if (act) e = funnel_r(pq[(i64)c * tk.nbp + blk], pq[(i64)c * tk.nbp + blk + 1], sh);
+                if (act) e = funnel_r(pq[(i64)blk * kPeqStride + c], pq[(i64)(blk + 1) * kPeqStride + c], sh);
                 eqw[c] = e;
             }
         }

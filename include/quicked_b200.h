@@ -86,6 +86,10 @@ int qb200_upload_device(qb200_ctx_t *ctx, const qb200_batch_t *device_batch);   
 int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params);                  /* results stay in HBM           */
 int qb200_download(qb200_ctx_t *ctx, qb200_results_t *host_results);
 int qb200_get_stats(qb200_ctx_t *ctx, qb200_stats_t *stats);
+/* After a QUICKED run: the stage-1 WindowEd(S) result of every pair of the batch — its score (the first alignment
+ * bound, reference quicked.c:178-199 `aligner->score` after run_windowed_score) and its count of high-error windows
+ * (reference bpm_windowed.c:555-557).  Either pointer may be NULL.  n must equal the batch's n_pairs. */
+int qb200_get_bounds(qb200_ctx_t *ctx, int32_t *bound, int32_t *high_error_windows, int64_t n);
 
 /* --- one call, host in / host out: what a reference caller's batch loop is replaced by --- */
 int qb200_align_batch(qb200_ctx_t *ctx, const quicked_params_t *params,

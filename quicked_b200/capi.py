@@ -25,7 +25,7 @@ QB200_ERR_NO_DEVICE, QB200_ERR_CUDA, QB200_ERR_ARG, QB200_ERR_OOM, QB200_ERR_CAP
 EXPORTS = ["quicked_check_error", "quicked_status_msg", "quicked_default_params", "quicked_new", "quicked_free",
            "quicked_align", "qb200_device_count", "qb200_create", "qb200_destroy", "qb200_set_stream",
            "qb200_set_workspace_limit", "qb200_last_error", "qb200_upload", "qb200_upload_device", "qb200_run",
-           "qb200_download", "qb200_get_stats", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
+           "qb200_download", "qb200_get_stats", "qb200_get_bounds", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
            "qb200_generate_pairs", "qb200_measure_int_peak"]
 
 
@@ -95,6 +95,7 @@ def load():
     L.qb200_run.argtypes = [C.c_void_p, C.POINTER(Params)]
     L.qb200_download.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.qb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.qb200_get_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     L.qb200_align_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Batch), C.POINTER(Results)]
     L.qb200_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qb200_host_alloc.restype = C.c_void_p
@@ -255,6 +256,12 @@ class BatchAligner:
         v = C.c_double()
         self._check(self._lib.qb200_measure_int_peak(self._h, C.byref(v)), "qb200_measure_int_peak")
         return v.value
+
+    def bounds(self):
+        """stage-1 WindowEd(S) score and high-error-window count per pair of the last QUICKED run"""
+        b = np.empty(self._n, np.int32); h = np.empty(self._n, np.int32)
+        self._check(self._lib.qb200_get_bounds(self._h, b.ctypes.data, h.ctypes.data, self._n), "qb200_get_bounds")
+        return b, h
 
     def stats(self):
         s = Stats()

@@ -89,7 +89,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
         for (int c = lane; c < 64; c += 32) {
             const int col = col0 + c;
             unsigned char code = 4;
-            if (col < tk.n) code = tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col];
+            if (col < tk.n) code = (tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col]) & 7;
             s_txt[c] = code;
         }
 #pragma unroll
@@ -261,7 +261,7 @@ k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ li
     __syncwarp();
     u64 ws = 0;
     for (int col = 0; col < ncols; ++col) {
-        unsigned char code = tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col];
+        unsigned char code = (tk.rev ? tcodes[tk.n - 1 - col] : tcodes[col]) & 7;
         u32 cin = 0, hp_carry = 1;
         const bool store_col = FULL && ((col & 63) != 63);
         for (int j0 = first; j0 <= last; j0 += 32) {
@@ -403,26 +403,32 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
             st_hi = max(st_hi, last);
             // band index of the last pattern block when its carry-out sits below bit 63 (level_mask, bpm_banded.c:88-102)
             const int jl = mmod ? (nblk - 1 - pos_v) : -1;
-            for (int c0 = 0; c0 < nc; c0 += 16) {
-                // sixteen columns' codes: one aligned 16-byte load (realigned in registers), two chunks ahead in flight
-                u32 cw[4];
+            // eight columns per loop body (the body has to stay well inside the 32 KB instruction cache); their codes
+            // come from one aligned 16-byte load per 16 columns, realigned in registers, two chunks ahead in flight
+            uint4 cr = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < nc; c0 += 8) {
+                u32 w0, w1;
                 if (rev) {
+                    w0 = w1 = 0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
+                    for (int k = 0; k < 8; ++k) {
                         const int col = col0 + c0 + k;
                         const u32 c = (c0 + k < nc) ? (u32)tcodes[n - 1 - col] : 4u;
-                        if ((k & 3) == 0) cw[k >> 2] = c; else cw[k >> 2] |= c << (8 * (k & 3));
+                        if (k < 4) w0 |= c << (8 * k); else w1 |= c << (8 * (k - 4));
                     }
                 } else {
-                    const uint4 c2 = __ldg(cvec + (((col0 + c0) >> 4) + 2));
-                    const uint4 r = realign16(ccur, cnxt, csh);
-                    cw[0] = r.x; cw[1] = r.y; cw[2] = r.z; cw[3] = r.w;
-                    ccur = cnxt; cnxt = c2;
+                    if (!(c0 & 8)) {
+                        const uint4 c2 = __ldg(cvec + (((col0 + c0) >> 4) + 2));
+                        cr = realign16(ccur, cnxt, csh);
+                        ccur = cnxt; cnxt = c2;
+                    }
+                    w0 = (c0 & 8) ? cr.z : cr.x; w1 = (c0 & 8) ? cr.w : cr.y;
                 }
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
+                for (int k = 0; k < 8; ++k) {
                     if (c0 + k < nc) {
-                        const int code = (int)((cw[k >> 2] >> (8 * (k & 3))) & 7u);
+                        const int code = (int)(((k < 4 ? w0 : w1) >> (8 * (k & 3))) & 7u);
                         ulonglong2 *dst = mat + (i64)(col0 + c0 + k + 1) * cs;
                         u32 hp = 1, hm = 0;
 #pragma unroll

@@ -109,6 +109,16 @@ __device__ __forceinline__ int enc_base(unsigned c)
     return code;
 }
 
+// Stored code byte = enc_base | kCodeOdd when the character is not one of "ACGTN" (upper case): on the others the
+// encoding is injective, so for two unflagged characters "same code" and "same raw byte" are the same statement —
+// the WindowEd walk then prices a diagonal step from the match mask instead of loading both raw bytes.
+constexpr unsigned kCodeOdd = 8u;
+__device__ __forceinline__ unsigned enc_stored(unsigned c)
+{
+    const bool plain = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | (c == 'N');
+    return (unsigned)enc_base(c) | (plain ? 0u : kCodeOdd);
+}
+
 // One Myers block update with bit-63 carry-out (reference bpm_commons.h:82-101).
 __device__ __forceinline__ void myers_step(u64 eq, u64 &pv, u64 &mv, u32 hp_in, u32 hm_in, u32 &hp_out, u32 &hm_out)
 {
@@ -160,7 +170,8 @@ __device__ __forceinline__ void myers_step_at(u64 eq, u64 &pv, u64 &mv, u32 hp_i
     mv = ph & xv;
 }
 
-// PEQ tables are stored [block][kPeqStride] (5 match masks + 1 pad word = 48 bytes per 64-row block, 16-byte aligned):
+// PEQ tables are stored [block][kPeqStride] (5 match masks + the mask of rows holding a character outside "ACGTN"
+// = 48 bytes per 64-row block, 16-byte aligned):
 // everything a thread needs for one block is three 16-byte loads from two DRAM sectors.
 constexpr int kPeqStride = 6;
 

@@ -87,7 +87,7 @@ struct qb200_ctx {
     std::vector<PairRec> h_pairs;
     std::vector<PeqJob> h_peqjobs;
     i64 peq_words = 0, cells = 0;
-    DevBuf d_raw, d_codes, d_pairs, d_peq, d_peqjobs;
+    DevBuf d_raw, d_codes, d_pairs, d_peq, d_peqjobs, d_pairodd;
     // per-run
     DevBuf d_bound, d_hew, d_score, d_status, d_textlen, d_cigoff, d_cigar, d_counters, d_scan_tmp;
     DevBuf d_leaves, d_leafout, d_pairleaves, d_work, d_bandout, d_matrix, d_scores, d_state, d_ops, d_ranges;
@@ -188,7 +188,7 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
         if (r.m > 0 && r.n > 0) {
             ops_words += (r.m + r.n + 15) / 16;
             max_n = std::max(max_n, r.n);
-            PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = words;
+            PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = words; j.t_off = r.t_off; j.n = r.n; j.flag = (int)i;
             ctx->h_peqjobs.push_back(j);
             words += (i64)kPeqStride * r.nbp;
             cells += (i64)r.m * r.n;
@@ -373,7 +373,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
     for (int k = 0; k < qb200_ctx::kWorkers; ++k) if (ctx->child[k]) { qb200_destroy(ctx->child[k]); ctx->child[k] = nullptr; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->d_raw, &ctx->d_codes, &ctx->d_pairs, &ctx->d_peq, &ctx->d_peqjobs, &ctx->d_bound, &ctx->d_hew,
+    for (DevBuf *b : {&ctx->d_raw, &ctx->d_codes, &ctx->d_pairs, &ctx->d_peq, &ctx->d_peqjobs, &ctx->d_pairodd, &ctx->d_bound, &ctx->d_hew,
                       &ctx->d_score, &ctx->d_status, &ctx->d_textlen, &ctx->d_cigoff, &ctx->d_cigar, &ctx->d_counters,
                       &ctx->d_scan_tmp, &ctx->d_leaves, &ctx->d_leafout, &ctx->d_pairleaves, &ctx->d_work, &ctx->d_bandout,
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
@@ -508,9 +508,12 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
             ctx->stats.kernel_launches++;
         }
         CK(ctx->d_peq.reserve((size_t)ctx->peq_words * 8 + 64));
+        CK(ctx->d_pairodd.reserve((size_t)n + 16));
+        CK(cudaMemsetAsync(ctx->d_pairodd.p, 1, (size_t)n + 16, ctx->stream));      // pairs without a job (an empty side) never reach the kernels
         const int nj = (int)ctx->h_peqjobs.size();
         if (nj) {
-            k_build_peq<<<(nj + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_peqjobs.as<PeqJob>(), nj, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>());
+            k_build_peq<<<(nj + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_peqjobs.as<PeqJob>(), nj, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
+                                                               ctx->d_pairodd.as<unsigned char>());
             CK(cudaGetLastError());
             ctx->stats.kernel_launches++;
         }
@@ -570,19 +573,20 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         if (const char *e = getenv("QB200_WS_CTAS")) ctas = std::max(1, std::min(atoi(e), (int)kWsCtasPerSm));
         const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * ctas);   // persistent: one wave
         CK(ctx->d_quad.reserve((size_t)blocks * kWsThreads * kWsQuadSlots * 8));
-        {   // 10 KB of shared memory per CTA: keep the carve-out just above what the resident CTAs need, the rest is L1
-            // for the text codes, raw bytes and match masks (measured: 5.75 vs 6.18 ms per 400 k pairs with the default)
-            int carve = (ctas * 11 * 100 + 227) / 228 + 1;
+        // Batches with texts of >= 128 characters have full windows: the SLIM kernel keeps their quadrants in shared
+        // memory (43.5 KB per CTA).  Shorter reads only ever run non-full windows, whose quadrant lives in the L2
+        // scratch: there the 10 KB kernel with most of the SM left as L1 is the faster one (C1: 4.2 vs 5.6 ms per 4 M).
+        const bool slim = ctx->max_n >= 128;
+        auto kern = prm.force_scalar ? (slim ? k_windowed21_score<false, true> : k_windowed21_score<false, false>)
+                                     : (slim ? k_windowed21_score<true, true> : k_windowed21_score<true, false>);
+        {   // carve out what the resident CTAs need (+1 KB per CTA of system use), the rest stays L1
+            int carve = std::min(100, (ctas * (slim ? 45 : 11) * 100 + 227) / 228 + 1);
             if (const char *e = getenv("QB200_WS_CARVE")) carve = atoi(e);
-            cudaFuncSetAttribute(k_windowed21_score<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(k_windowed21_score<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         }
-        if (prm.force_scalar)
-            k_windowed21_score<false><<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(), ctx->d_quad.as<u64>());
-        else
-            k_windowed21_score<true><<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(), ctx->d_quad.as<u64>());
+        kern<<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+            ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(),
+            ctx->d_quad.as<u64>(), ctx->d_pairodd.as<unsigned char>());
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
     }
@@ -804,7 +808,7 @@ int build_tables(qb200_ctx *ctx, std::vector<PeqJob> &jobs)
     CK(ctx->d_jobs2.reserve(sizeof(PeqJob) * jobs.size()));
     CK(cudaMemcpyAsync(ctx->d_jobs2.p, jobs.data(), sizeof(PeqJob) * jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
     const int nj = (int)jobs.size();
-    k_build_peq<<<(nj + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_jobs2.as<PeqJob>(), nj, ctx->d_codes.as<unsigned char>(), ctx->d_peq2.as<u64>());
+    k_build_peq<<<(nj + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_jobs2.as<PeqJob>(), nj, ctx->d_codes.as<unsigned char>(), ctx->d_peq2.as<u64>(), nullptr);
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
     return 0;
@@ -1295,6 +1299,18 @@ int qb200_get_stats(qb200_ctx_t *ctx, qb200_stats_t *stats)
 {
     if (!ctx || !stats) return QB200_ERR_ARG;
     *stats = ctx->stats;
+    return 0;
+}
+
+int qb200_get_bounds(qb200_ctx_t *ctx, int32_t *bound, int32_t *high_error_windows, int64_t n)
+{
+    if (!ctx || n != ctx->n_pairs) return QB200_ERR_ARG;
+    if (n == 0) return 0;
+    if (ctx->d_bound.cap < (size_t)n * 4 || ctx->d_hew.cap < (size_t)n * 4) { ctx->err = "no QUICKED run on this batch yet"; return QB200_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    if (bound) CK(cudaMemcpyAsync(bound, ctx->d_bound.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (high_error_windows) CK(cudaMemcpyAsync(high_error_windows, ctx->d_hew.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

@@ -50,7 +50,7 @@ k_quicked_fused(const PairRec *__restrict__ pairs, int n_pairs, const unsigned c
         const PairRec pr = pairs[i];
         if (pr.m <= 0 || pr.n <= 0) { done[i] = 0; continue; }
         int score = 0, hew = 0;
-        ws21_pair<SSE>(pr, codes, raw, peq, s_thr, qpv, qmv, nthr, hew_lim, score, hew, ws_w);
+        ws21_pair<SSE, false>(pr, codes, raw, peq, s_thr, qpv, qmv, nthr, nullptr, false, hew_lim, score, hew, ws_w);
         bound[i] = score; hew_out[i] = hew;
         const unsigned maxlen = (unsigned)max(pr.m, pr.n);
         const BandGeom g = band_geometry(pr.m, pr.n, score);

@@ -7,7 +7,7 @@
 
 namespace qb {
 
-// Elementwise: codes[i] = enc(raw[i]).  16 bytes per thread, fully coalesced.  HBM-bound: 2 B/char.
+// Elementwise: codes[i] = enc_stored(raw[i]) (base code, bit 3 = not a plain ACGTN character).  16 bytes per thread, fully coalesced.  HBM-bound: 2 B/char.
 __global__ void __launch_bounds__(256) k_encode(const uint4 *__restrict__ raw, uint4 *__restrict__ codes, i64 n_vec)
 {
     const i64 stride = (i64)gridDim.x * blockDim.x;
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) k_encode(const uint4 *__restrict__ raw, u
         for (int w = 0; w < 4; ++w) {
             u32 o = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) o |= (u32)enc_base((in[w] >> (8 * b)) & 0xffu) << (8 * b);
+            for (int b = 0; b < 4; ++b) o |= (u32)enc_stored((in[w] >> (8 * b)) & 0xffu) << (8 * b);
             out[w] = o;
         }
         codes[i] = make_uint4(out[0], out[1], out[2], out[3]);
@@ -31,12 +31,18 @@ struct PeqJob {
     int m;         // (sub-)pattern length
     int rev;       // 1: table of the reversed (sub-)pattern
     i64 peq_off;   // destination, u64 index; layout [nbp][kPeqStride], nbp = ceil(m/64)+2
+    i64 t_off = 0; // when flag >= 0: the pair's text, scanned for characters outside "ACGTN"
+    int n = 0;
+    int flag = -1; // index into the per-pair "odd characters" flags, -1: none wanted
 };
 
 // One warp per table.  Each iteration covers one 64-row block: two coalesced 32-byte reads of codes, five ballots
 // each.  Rows >= m inside the last block match every code (reference bpm_banded.c:77-86); the two extra blocks are 0.
+// With job.flag >= 0 the warp also reports whether the pattern or the text holds a character outside "ACGTN" (the
+// WindowEd(S) kernel prices diagonal steps from the match masks only for pairs without any).
 __global__ void __launch_bounds__(256) k_build_peq(const PeqJob *__restrict__ jobs, int n_jobs,
-                                                   const unsigned char *__restrict__ codes, u64 *__restrict__ peq)
+                                                   const unsigned char *__restrict__ codes, u64 *__restrict__ peq,
+                                                   unsigned char *__restrict__ odd_flags)
 {
     const int warp = (int)(((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -44,26 +50,45 @@ __global__ void __launch_bounds__(256) k_build_peq(const PeqJob *__restrict__ jo
     const PeqJob job = jobs[warp];
     const int nblk = (job.m + 63) >> 6, nbp = nblk + 2;
     u64 *dst = peq + job.peq_off;
+    u32 any_odd = 0;
     for (int blk = 0; blk < nbp; ++blk) {
-        u32 lo[kAlpha], hi[kAlpha];
+        u32 lo[kPeqStride], hi[kPeqStride];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int row = blk * 64 + half * 32 + lane;
             int code = -1;                       // -1: beyond the padded pattern (no match), 5: padding row (all match)
-            if (row < job.m) code = codes[job.src_off + (job.rev ? (job.m - 1 - row) : row)];
-            else if (blk < nblk) code = 5;
+            bool odd = false;                    // row holds a character outside "ACGTN"
+            if (row < job.m) {
+                const unsigned sc = codes[job.src_off + (job.rev ? (job.m - 1 - row) : row)];
+                code = (int)(sc & 7u); odd = (sc & kCodeOdd) != 0;
+            } else if (blk < nblk) code = 5;
 #pragma unroll
             for (int c = 0; c < kAlpha; ++c) {
                 const u32 b = __ballot_sync(kFull, code == c || code == 5);
                 if (half == 0) lo[c] = b; else hi[c] = b;
             }
+            const u32 b = __ballot_sync(kFull, odd);
+            if (half == 0) lo[kAlpha] = b; else hi[kAlpha] = b;
+            any_odd |= b;
         }
         if (lane < kPeqStride) {
-            u32 l = 0, h = 0;                    // lane 5: the pad word
+            u32 l = 0, h = 0;                    // lane 5: the mask of rows with an odd character
 #pragma unroll
-            for (int c = 0; c < kAlpha; ++c) if (lane == c) { l = lo[c]; h = hi[c]; }
+            for (int c = 0; c < kPeqStride; ++c) if (lane == c) { l = lo[c]; h = hi[c]; }
             dst[(i64)blk * kPeqStride + lane] = ((u64)h << 32) | l;
         }
+    }
+    if (job.flag >= 0) {
+        const unsigned long long t0 = (unsigned long long)(codes + job.t_off), t1 = t0 + (unsigned long long)job.n, a0 = t0 & ~3ull;
+        u32 acc = 0;
+        for (unsigned long long a = a0 + 4ull * lane; a < t1; a += 128) {
+            u32 msk = 0x08080808u;                                   // kCodeOdd of the bytes that belong to the text
+            if (a < t0) msk <<= 8 * (unsigned)(t0 - a);
+            if (a + 4 > t1) msk &= 0x08080808u >> (8 * (unsigned)(a + 4 - t1));
+            acc |= *reinterpret_cast<const u32 *>(a) & msk;
+        }
+        any_odd |= __ballot_sync(kFull, acc != 0);
+        if (lane == 0) odd_flags[job.flag] = any_odd ? 1 : 0;
     }
 }
 

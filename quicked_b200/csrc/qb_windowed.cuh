@@ -22,27 +22,45 @@ constexpr int kWsCtasPerSm = 6;                 // up to 768 resident threads pe
 constexpr int kWsResidentCtas = 4;              // CTAs per SM actually launched (scratch = 16.6 KB per resident CTA-thread group)
 constexpr int kWsQuadSlots = 65 * 2;            // u64 slots per thread in the quadrant scratch ([slot][thread] layout)
 
-// Sixteen columns of a FULL window (2 words x 128 columns, walk quadrant = word 1 of columns 64..128), the case of all
-// but the first/last windows of a pair.  MODE 0: nothing is stored, 1: columns >= 63 are stored, 2: all are stored.
-// cw: the sixteen columns' codes, one per byte.
-template <bool SSE, int MODE>
-__device__ __forceinline__ void ws_full_group16(const uint4 cw, int c0, u32 top_in, const u64 *weq,
-                                                u64 &pv0, u64 &mv0, u64 &pv1, u64 &mv1, u64 &pv1_prev, u64 &mv1_prev,
-                                                u64 *qpv, u64 *qmv, i64 nthr)
+// SLIM: instead of the 64-row words of Pv and Mv, column s (1..64) of the quadrant keeps the walk's DECISION for the
+// 16 rows around its diagonal (see ws21_pair), two bit planes packed into one u32 of shared memory at sq[s * T]:
+//   plane a (bits 0..15)  = Pv[s] | (~Mv[s-1] & ~Eq[s])        plane b (bits 16..31) = ~Pv[s] & (Mv[s-1] | ~Eq[s])
+//   (a,b) = (1,0) deletion, (0,1) insertion, (1,1) mismatch, (0,0) codes match   — the order of bpm_windowed.c:520-545
+// for rows s-9..s+6, read at slice index d = row - jp + 9 when the walk stands in column jp = s.
+__device__ __forceinline__ u32 slice16(u64 x, int lo)       // bits [lo, lo+16) of x, zero outside 0..63; -16 <= lo < 64
+{
+    const u64 y = lo >= 0 ? (x >> lo) : (x << (-lo));
+    return (u32)y & 0xffffu;
+}
+__device__ __forceinline__ u32 slim_entry(u64 pv, u64 mv_prev, u64 eq, int s)
+{
+    const u64 a = pv | ~(mv_prev | eq), b = ~pv & (mv_prev | ~eq);
+    return slice16(a, s - 9) | (slice16(b, s - 9) << 16);
+}
+
+// Eight columns of a FULL window (2 words x 128 columns; the walk's quadrant is word 1 of columns 64..128), the case
+// of all but the last one or two windows of a pair.  STORE 0: nothing is kept (columns 0..63), 1: Pv/Mv of word 1 go
+// to the L2/HBM scratch, 2: the walk decisions go to shared memory (SLIM).  w0/w1: the eight columns' code bytes.
+// The body is kept this small on purpose: the kernel's hot loop has to stay inside the 32 KB instruction cache.
+template <bool SSE, int STORE>
+__device__ __forceinline__ void ws_full_group8(u32 w0, u32 w1, int c0, u32 top_in, const u64 *weq,
+                                               u64 &pv0, u64 &mv0, u64 &pv1, u64 &mv1, u64 &pv1_prev, u64 &mv1_prev,
+                                               u64 *qpv, u64 *qmv, i64 nthr, u32 *sq)
 {
     constexpr int T = kWsThreads;
-    const u32 w[4] = {cw.x, cw.y, cw.z, cw.w};
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < 8; ++k) {
         const int c = c0 + k;
-        const u32 code = (w[k >> 2] >> (8 * (k & 3))) & 7u;
+        const u32 code = ((k < 4 ? w0 : w1) >> (8 * (k & 3))) & 7u;
         u32 hp_in0 = top_in;
-        if (SSE) hp_in0 = (c == 0) ? top_in : ((c == 1) ? 1u : (u32)((k & 1) ^ 1));   // c0 is a multiple of 16: parity(c) = parity(k)
+        if (SSE) hp_in0 = (c == 0) ? top_in : ((c == 1) ? 1u : (u32)((k & 1) ^ 1));   // c0 is a multiple of 8: parity(c) = parity(k)
         u32 hp, hm, o1, o2;
         myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
         if (SSE && c == 127) { pv1_prev = pv1; mv1_prev = mv1; }
-        myers_step(weq[(kAlpha + code) * T], pv1, mv1, hp, hm, o1, o2);
-        if (MODE == 2 || (MODE == 1 && c >= 63)) {
+        const u64 eq1 = weq[(kAlpha + code) * T], mv1_before = mv1;
+        myers_step(eq1, pv1, mv1, hp, hm, o1, o2);
+        if (STORE == 2) sq[(c - 63) * T] = slim_entry(pv1, mv1_before, eq1, c - 63);
+        if (STORE == 1) {
             qpv[(i64)(c - 63) * nthr] = pv1;
             qmv[(i64)(c - 63) * nthr] = mv1;
         }
@@ -51,10 +69,18 @@ __device__ __forceinline__ void ws_full_group16(const uint4 cw, int c0, u32 top_
 
 // WindowEd(S) of ONE pair by one thread (see k_windowed21_score).  weq: this thread's 10 shared-memory slots
 // (stride kWsThreads); qpv/qmv: this thread's quadrant scratch (slot stride nthr).
-template <bool SSE>
+//
+// SLIM: full windows (all but the last one or two of a pair) keep their quadrant in shared memory as 64 u32 of walk
+// decisions (slim_entry): the walk starts on the diagonal (row 63 of column 64) and only an insertion or a deletion
+// moves it off, so it stays within the 16 rows kept per column unless the 64-column window holds 8 more of one than
+// of the other (about 1 window in 10^4 at 10 % error).  If it does leave the slice, the window is simply recomputed
+// with the full 64-row quadrant in the L2/HBM scratch (the path non-full windows always take), so the result never
+// depends on the slice width.  The walk then touches global memory only for characters outside "ACGTN".
+template <bool SSE, bool SLIM>
 __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char *__restrict__ codes,
                                           const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, u64 *weq,
-                                          u64 *qpv, u64 *qmv, i64 nthr, int hew_lim, int &score_out, int &hew_out, u64 &ws)
+                                          u64 *qpv, u64 *qmv, i64 nthr, u32 *sq, bool slim_ok, int hew_lim, int &score_out,
+                                          int &hew_out, u64 &ws)
 {
     constexpr int T = kWsThreads;
         int score = 0, hew = 0;
@@ -63,6 +89,7 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
             const unsigned char *tc = codes + pr.t_off;
             const unsigned char *traw = raw + pr.t_off, *praw = raw + pr.p_off;
             const u64 *pq = peq + pr.peq_off;
+            bool wide = false;                               // this window left the slim slice: redo it with the full quadrant
             while (cv >= 0 && ch >= 0) {
                 // ---- window geometry (bpm_windowed.c:219-232) ----
                 const int v0 = max(cv - 127, 0), h0 = max(ch - 127, 0);
@@ -101,6 +128,7 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                     qmv[0] = 0;
                 }
                 const bool full = (words == 2 && cols == 128 && cv >= 127);      // => r0 == 64, cs == 64
+                const bool slim = SLIM && slim_ok && full && !wide;
                 // the window's codes come in as aligned 16-byte chunks (one load per 16 columns, one chunk ahead in
                 // flight) and are realigned in registers; the flat code buffer is readable 48 B past its end
                 const int csh = (int)((unsigned long long)(tc + h0) & 15ull);
@@ -108,92 +136,121 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                 uint4 ccur = __ldg(cvec), cnxt = __ldg(cvec + 1);
                 u32 code_last = 4;
                 if (full) {
+                    uint4 r = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-                    for (int g = 0; g < 3; ++g) {
-                        const uint4 c2 = __ldg(cvec + g + 2);
-                        const uint4 r = realign16(ccur, cnxt, csh);
-                        ccur = cnxt; cnxt = c2;
-                        ws_full_group16<SSE, 0>(r, g * 16, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
+                    for (int q = 0; q < 16; ++q) {           // sixteen groups of eight columns
+                        if (!(q & 1)) {
+                            const uint4 c2 = __ldg(cvec + min((q >> 1) + 2, 8));
+                            r = realign16(ccur, cnxt, csh);
+                            ccur = cnxt; cnxt = c2;
+                        }
+                        const u32 w0 = (q & 1) ? r.z : r.x, w1 = (q & 1) ? r.w : r.y;
+                        if (q < 8) {
+                            ws_full_group8<SSE, 0>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
+                            if (q == 7 && !slim) { qpv[0] = pv1; qmv[0] = mv1; }     // stored column 0: the state after window column 63
+                        } else if (slim) {
+                            ws_full_group8<SSE, 2>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
+                        } else {
+                            ws_full_group8<SSE, 1>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
+                        }
                     }
-                    {
-                        const uint4 c2 = __ldg(cvec + 5);
-                        const uint4 r = realign16(ccur, cnxt, csh);
-                        ccur = cnxt; cnxt = c2;
-                        ws_full_group16<SSE, 1>(r, 48, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
-                    }
-#pragma unroll 1
-                    for (int g = 4; g < 8; ++g) {
-                        const uint4 c2 = __ldg(cvec + min(g + 2, 8));
-                        const uint4 r = realign16(ccur, cnxt, csh);
-                        ccur = cnxt; cnxt = c2;
-                        ws_full_group16<SSE, 2>(r, g * 16, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr);
-                        if (g == 7) code_last = r.w >> 24;
-                    }
+                    code_last = r.w >> 24;
                 }
-                for (int c0 = full ? cols : 0; c0 < cols; c0 += 16) {
-                    const uint4 c2 = __ldg(cvec + (c0 >> 4) + 2);
-                    const uint4 r = realign16(ccur, cnxt, csh);
-                    ccur = cnxt; cnxt = c2;
-                    const u32 cw[4] = {r.x, r.y, r.z, r.w};
+                {
+                    uint4 r = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+                    for (int c0 = full ? cols : 0; c0 < cols; c0 += 8) {
+                        if (!(c0 & 8)) {
+                            const uint4 c2 = __ldg(cvec + (c0 >> 4) + 2);
+                            r = realign16(ccur, cnxt, csh);
+                            ccur = cnxt; cnxt = c2;
+                        }
+                        const u32 w0 = (c0 & 8) ? r.z : r.x, w1 = (c0 & 8) ? r.w : r.y;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const int c = c0 + k;
-                        if (c < cols) {
-                            const int code = (int)((cw[k >> 2] >> (8 * (k & 3))) & 7u);
-                            if (c == cols - 1) code_last = (u32)code;
-                            u32 hp_in0 = top_in;
-                            if (SSE && c > 0) hp_in0 = (c == 1) | ((c & 1) ^ 1);       // :348,:393,:424
-                            u32 hp, hm, o1, o2;
-                            myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
-                            if (words == 2) {
-                                if (SSE && c == cols - 1) { pv1_prev = pv1; mv1_prev = mv1; }
-                                if (SSE && cols == 1) { hp = 0; hm = 0; }              // uninitialised carry in the reference
-                                myers_step(weq[(kAlpha + code) * T], pv1, mv1, hp, hm, o1, o2);
-                            }
-                            if (c + 1 >= cs) {
-                                const i64 s = (i64)(c + 1 - cs) * nthr;
-                                qpv[s] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
-                                qmv[s] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
+                        for (int k = 0; k < 8; ++k) {
+                            const int c = c0 + k;
+                            if (c < cols) {
+                                const int code = (int)(((k < 4 ? w0 : w1) >> (8 * (k & 3))) & 7u);
+                                if (c == cols - 1) code_last = (u32)code;
+                                u32 hp_in0 = top_in;
+                                if (SSE && c > 0) hp_in0 = (c == 1) | ((c & 1) ^ 1);       // :348,:393,:424
+                                u32 hp, hm, o1, o2;
+                                myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
+                                if (words == 2) {
+                                    if (SSE && c == cols - 1) { pv1_prev = pv1; mv1_prev = mv1; }
+                                    if (SSE && cols == 1) { hp = 0; hm = 0; }              // uninitialised carry in the reference
+                                    myers_step(weq[(kAlpha + code) * T], pv1, mv1, hp, hm, o1, o2);
+                                }
+                                if (c + 1 >= cs) {
+                                    const i64 s = (i64)(c + 1 - cs) * nthr;
+                                    qpv[s] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
+                                    qmv[s] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
+                                }
                             }
                         }
                     }
                 }
-                ws += (u64)(words * cols);
                 if (SSE && words == 2 && !(cols & 1)) {
                     // look-ahead column of word 0 (:361) and the redone last column of word 1 (:428-444)
                     const int ti = h0 + cols;
-                    const int code_la = (ti < pr.n) ? (int)tc[ti] : 4;
+                    const int code_la = (ti < pr.n) ? (int)(tc[ti] & 7) : 4;
                     u64 lpv = pv0, lmv = mv0;
                     u32 hpL, hmL, o1, o2;
                     myers_step(weq[code_la * T], lpv, lmv, 1u, 0u, hpL, hmL);
                     pv1 = pv1_prev; mv1 = mv1_prev;
-                    myers_step(weq[(kAlpha + code_last) * T], pv1, mv1, hpL, hmL, o1, o2);
-                    const i64 s = (i64)(cols - cs) * nthr;
-                    qpv[s] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
-                    qmv[s] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
+                    const u64 eq1 = weq[(kAlpha + (code_last & 7u)) * T];
+                    myers_step(eq1, pv1, mv1, hpL, hmL, o1, o2);
+                    if (slim) sq[64 * T] = slim_entry(pv1, mv1_prev, eq1, 64);
+                    else {
+                        const i64 s = (i64)(cols - cs) * nthr;
+                        qpv[s] = (r0 >= 64) ? pv1 : funnel_r(pv0, pv1, r0);
+                        qmv[s] = (r0 >= 64) ? mv1 : funnel_r(mv0, mv1, r0);
+                    }
                 }
                 // ---- walk back through the non-overlapping 64 rows/columns (bpm_windowed.c:504-561): D, I, M, X ----
                 // The next column's words are prefetched one column ahead, and the raw-byte compare of a diagonal
                 // step (it only decides the cost, never the path) is consumed one step later.
                 int v = cv, h = ch, cost = 0;
                 int jp = h - h_stop + 1;                     // stored column index of Pv for the current h
-                u64 dp = qpv[(i64)jp * nthr], im = qmv[(i64)(jp - 1) * nthr];
-                u64 dpn = 0, imn = 0;
-                if (jp >= 2) { dpn = qpv[(i64)(jp - 1) * nthr]; imn = qmv[(i64)(jp - 2) * nthr]; }
                 u32 pend_t = 0, pend_p = 0;
-                while (v >= v_stop && jp >= 1) {
-                    const int bit = v - v_stop;
-                    cost += (pend_t != pend_p);
-                    pend_t = pend_p = 0;
-                    if ((dp >> bit) & 1ull) { ++cost; --v; }
-                    else {
-                        if ((im >> bit) & 1ull) ++cost;
-                        else { pend_t = traw[h]; pend_p = praw[v]; --v; }
-                        --h; --jp;
-                        dp = dpn; im = imn;
-                        if (jp >= 2) { dpn = qpv[(i64)(jp - 1) * nthr]; imn = qmv[(i64)(jp - 2) * nthr]; }
+                if (slim) {
+                    // a diagonal step costs 1 iff the raw characters differ (bpm_windowed.c:540); slim pairs hold only
+                    // "ACGTN", for which that is the same as "the codes differ": no global memory in this loop
+                    u32 w = sq[64 * T], wn = sq[63 * T];
+                    int d = 8;                               // slice index of the current cell: row - jp + 9
+                    while (v >= v_stop && jp >= 1 && (unsigned)d < 16u) {
+                        const u32 a = (w >> d) & 1u, b = (w >> (16 + d)) & 1u;
+                        cost += (int)(a | b);
+                        const int del = (int)(a & ~b), ins = (int)(b & ~a);
+                        v -= 1 - ins;                        // a deletion or a diagonal step consumes a pattern row
+                        d += ins - del;
+                        if (!del) {                          // an insertion or a diagonal step consumes a text column
+                            --h; --jp;
+                            w = wn;
+                            wn = sq[max(jp - 1, 1) * T];
+                        }
+                    }
+                    if ((unsigned)d >= 16u) { wide = true; continue; }     // left the slice: same window again, full quadrant
+                } else {
+                    u64 dp = qpv[(i64)jp * nthr], im = qmv[(i64)(jp - 1) * nthr];
+                    u64 dpn = 0, imn = 0;
+                    if (jp >= 2) { dpn = qpv[(i64)(jp - 1) * nthr]; imn = qmv[(i64)(jp - 2) * nthr]; }
+                    while (v >= v_stop && jp >= 1) {
+                        const int bit = v - v_stop;
+                        cost += (pend_t != pend_p);
+                        pend_t = pend_p = 0;
+                        if ((dp >> bit) & 1ull) { ++cost; --v; }
+                        else {
+                            if ((im >> bit) & 1ull) ++cost;
+                            else { pend_t = traw[h]; pend_p = praw[v]; --v; }
+                            --h; --jp;
+                            dp = dpn; im = imn;
+                            if (jp >= 2) { dpn = qpv[(i64)(jp - 1) * nthr]; imn = qmv[(i64)(jp - 2) * nthr]; }
+                        }
                     }
                 }
+                wide = false;
+                ws += (u64)(words * cols);
                 cost += (pend_t != pend_p);
                 if (cost > hew_lim) ++hew;
                 score += cost;
@@ -205,14 +262,15 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
         score_out = score; hew_out = hew;
 }
 
-template <bool SSE>
+template <bool SSE, bool SLIM>
 __global__ void __launch_bounds__(kWsThreads, kWsCtasPerSm)
 k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigned char *__restrict__ codes,
                    const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, int hew_threshold,
                    int *__restrict__ bound, int *__restrict__ hew_out, u64 *__restrict__ counters,
-                   u64 *__restrict__ quad)
+                   u64 *__restrict__ quad, const unsigned char *__restrict__ pair_odd)
 {
     __shared__ u64 s_weq[2 * kAlpha * kWsThreads];          // [2*5][T] window-aligned match masks
+    __shared__ u32 s_slim[SLIM ? 65 * kWsThreads : 1];      // [65][T] slim quadrant of full windows (see ws21_pair)
     const int T = kWsThreads, t = threadIdx.x;
     u64 *weq = s_weq + t;
     const i64 gtid = (i64)blockIdx.x * T + t, nthr = (i64)gridDim.x * T;
@@ -225,7 +283,7 @@ k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigne
     for (i64 i = gtid; i < n_pairs; i += nthr) {
         const PairRec pr = pairs[i];
         int score = 0, hew = 0;
-        ws21_pair<SSE>(pr, codes, raw, peq, weq, qpv, qmv, nthr, hew_lim, score, hew, ws);
+        ws21_pair<SSE, SLIM>(pr, codes, raw, peq, weq, qpv, qmv, nthr, s_slim + (SLIM ? t : 0), SLIM && pair_odd[i] == 0, hew_lim, score, hew, ws);
         bound[i] = score;
         hew_out[i] = hew;
     }
@@ -305,7 +363,7 @@ k_windowed_warp(const WinTask *__restrict__ tasks, int n_tasks, const unsigned c
             int col_t = h0 + c;
             if (la && lane == 1) col_t = h0 + cols - 1;
             int code = 4;
-            if (col_t < tk.n) code = tk.rev ? tc[tk.n - 1 - col_t] : tc[col_t];
+            if (col_t < tk.n) code = (tk.rev ? tc[tk.n - 1 - col_t] : tc[col_t]) & 7;
             if (sse && c == cols - 1) { pv_prev = pv; mv_prev = mv; }
             if (la && lane == 1) { pv = pv_prev; mv = mv_prev; }
             u64 eq = eqw[0];

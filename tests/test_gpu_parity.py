@@ -273,6 +273,35 @@ def test_fused_and_planned_paths_agree(oracle, fused, monkeypatch):
     a.close()
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_stage1_bounds_match_oracle(oracle, fused, monkeypatch):
+    """WindowEd(S) score and high-error-window count of every pair (qb200_get_bounds) against the oracle's
+    WindowEd(2,1): plain reads, 20 % error, long indels (walks that leave the slim quadrant slice and are redone with
+    the full one), lower case / IUPAC characters on either side (raw-byte compare of equal codes)."""
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_FUSED", fused)
+    rng = np.random.default_rng(77)
+    pairs = generate_pairs(150, 1000, 0.1, seed=61) + generate_pairs(40, 3000, 0.2, seed=62) + generate_pairs(100, 100, 0.05, seed=63) + \
+        generate_pairs(40, 2000, 0.05, seed=64, indels=(6, 40)) + generate_pairs(30, 700, 0.3, seed=65)
+    odd = []
+    for p, t in generate_pairs(60, 900, 0.08, seed=66):
+        p = bytearray(p.encode() if isinstance(p, str) else p); t = bytearray(t.encode() if isinstance(t, str) else t)
+        for buf in (p, t):
+            for k in rng.integers(0, len(buf), size=40):
+                c = chr(buf[k])
+                buf[k] = ord(rng.choice(list(c.lower() + "NRYnX-")))
+        odd.append((bytes(p), bytes(t)))
+    pairs += odd
+    a = qb.BatchAligner(device=0)
+    for fs in (False, True):
+        a.align(pairs, algo=0, force_scalar=fs)
+        bound, hew = a.bounds()
+        for i, (p, t) in enumerate(pairs):
+            exp = oracle.windowed_score(p, t, 2, 1, 40, not fs)
+            assert (int(bound[i]), int(hew[i])) == exp, (i, fs, len(p), len(t))
+    a.close()
+
+
 def test_edge_cases_match_oracle(gpu, oracle):
     """empty batch, single characters, identical / unrelated sequences, all-N, very unequal lengths, lowercase"""
     assert gpu.align([]) == []

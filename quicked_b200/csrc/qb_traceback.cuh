@@ -84,6 +84,11 @@ __device__ __forceinline__ void traceback_walk_thread(int m, int n, i64 cutoff, 
         }
         return mat[(i64)c * cs + (i64)wd * wsd];
     };
+    // eP: the entry the walk will most likely need next (column h-1, the word of row v-1), fetched one step early so
+    // that two dependent HBM round trips are in flight per thread instead of one (a second look-ahead entry was
+    // measured slower: 11.6 vs 10.6 ms per 1M pairs at 1 kbp)
+    int keyP = -1;
+    ulonglong2 eP = make_ulonglong2(0, 0);
     while (v >= 0 && h >= 0) {
         const int ev = v - 64 * ((h >> 6) - prolog);
         const int evr = v - 64 * (((h + 1) >> 6) - prolog);
@@ -93,19 +98,28 @@ __device__ __forceinline__ void traceback_walk_thread(int m, int n, i64 cutoff, 
         const int fR = (h + 1) * B + wr, fL = h * B + wl;
         if (fR != keyR) {
             if (fR == keyL) eR = eL;
+            else if (fR == keyP) eR = eP;
             else if ((unsigned)wr < (unsigned)B) eR = fetch(h + 1, wr);
             else eR = fR >= 0 ? fetch(fR / B, fR % B) : make_ulonglong2(0, 0);
             keyR = fR;
         }
         if (fL != keyL) {
-            if ((unsigned)wl < (unsigned)B) eL = fetch(h, wl);
+            if (fL == keyP) eL = eP;
+            else if ((unsigned)wl < (unsigned)B) eL = fetch(h, wl);
             else eL = fL >= 0 ? fetch(fL / B, fL % B) : make_ulonglong2(0, 0);
             keyL = fL;
+        }
+        // the raw characters of this cell and the next column's entry: independent of eR / eL, so all in flight together
+        const u32 ct = traw[h], cp = praw[v];
+        if (h > 0 && v > 0) {
+            const int wp = ((v - 1) - 64 * (((h - 1) >> 6) - prolog)) / 64;
+            const int fP = (h - 1) * B + wp;
+            if (fP != keyP && (unsigned)wp < (unsigned)B) { eP = fetch(h - 1, wp); keyP = fP; }
         }
         const bool isD = (eR.x >> (evr & 63)) & 1ull;
         const bool isI = (eL.y >> (ev & 63)) & 1ull;
         int op = isD ? OP_D : OP_I;
-        if (!isD && !isI) op = (traw[h] == praw[v]) ? OP_M : OP_X;     // RAW byte compare (bpm_banded.c:1012)
+        if (!isD && !isI) op = (ct == cp) ? OP_M : OP_X;     // RAW byte compare (bpm_banded.c:1012)
         w.emit(op);
         v -= (isD || !isI) ? 1 : 0;          // D and diagonal consume a pattern row
         h -= isD ? 0 : 1;                    // I and diagonal consume a text column

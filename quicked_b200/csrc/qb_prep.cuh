@@ -7,20 +7,22 @@
 
 namespace qb {
 
-// Elementwise: codes[i] = enc_stored(raw[i]) (base code, bit 3 = not a plain ACGTN character).  16 bytes per thread, fully coalesced.  HBM-bound: 2 B/char.
+// Elementwise: codes[i] = enc_stored(raw[i]) (base code, bit 3 = not a plain ACGTN character).  16 bytes per thread,
+// fully coalesced; the 256-entry table sits in shared memory (the arithmetic form costs ~25 integer ops per byte
+// and made this kernel ALU-bound at 4x its HBM time).  HBM-bound: 2 B/char.
 __global__ void __launch_bounds__(256) k_encode(const uint4 *__restrict__ raw, uint4 *__restrict__ codes, i64 n_vec)
 {
+    __shared__ unsigned char lut[256];
+    lut[threadIdx.x] = (unsigned char)enc_stored(threadIdx.x);
+    __syncthreads();
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
         const uint4 r = raw[i];
         u32 in[4] = {r.x, r.y, r.z, r.w}, out[4];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            u32 o = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) o |= (u32)enc_stored((in[w] >> (8 * b)) & 0xffu) << (8 * b);
-            out[w] = o;
-        }
+        for (int w = 0; w < 4; ++w)
+            out[w] = (u32)lut[in[w] & 0xffu] | ((u32)lut[(in[w] >> 8) & 0xffu] << 8) | ((u32)lut[(in[w] >> 16) & 0xffu] << 16) |
+                     ((u32)lut[in[w] >> 24] << 24);
         codes[i] = make_uint4(out[0], out[1], out[2], out[3]);
     }
 }

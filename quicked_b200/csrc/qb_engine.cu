@@ -70,6 +70,29 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Growable page-locked host array (contents are not kept across a growth).
+template <class T> struct PinnedArray {
+    T *p = nullptr;
+    size_t cap = 0, n = 0;
+    bool resize(size_t count)
+    {
+        if (count > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            const size_t want = count + count / 8 + 64;
+            if (cudaHostAlloc(reinterpret_cast<void **>(&p), want * sizeof(T), cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+            cap = want;
+        }
+        n = count;
+        return true;
+    }
+    T *data() { return p; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
+};
+
 enum Stage { ST_PREP = 0, ST_WS, ST_WL, ST_BANDED, ST_FILL, ST_TRACE, ST_CIGAR, ST_PLAN, ST_FUSED, ST_COUNT };
 
 }  // namespace
@@ -84,8 +107,8 @@ struct qb200_ctx {
     // uploaded batch
     i64 n_pairs = 0, raw_bytes = 0;
     const unsigned char *d_raw_ext = nullptr;   // upload_device: caller-owned characters
-    std::vector<PairRec> h_pairs;
-    std::vector<PeqJob> h_peqjobs;
+    PinnedArray<PairRec> h_pairs;          // pinned: its H2D copy must not hold the driver lock of a pageable copy
+    PinnedArray<unsigned char> h_stage;    // pinned staging of results bound for pageable caller memory
     i64 peq_words = 0, cells = 0;
     DevBuf d_raw, d_codes, d_pairs, d_peq, d_peqjobs, d_pairodd;
     // per-run
@@ -169,9 +192,7 @@ struct Span {
 int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t *plen, const int64_t *toff,
                        const int32_t *tlen, i64 seqs_bytes)
 {
-    ctx->h_pairs.resize((size_t)n);
-    ctx->h_peqjobs.clear();
-    ctx->h_peqjobs.reserve((size_t)n);
+    if (!ctx->h_pairs.resize((size_t)n)) { ctx->err = "out of pinned host memory"; return QB200_ERR_OOM; }
     i64 words = 0, cells = 0, ops_words = 0;
     int max_n = 0;
     for (i64 i = 0; i < n; ++i) {
@@ -188,8 +209,6 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
         if (r.m > 0 && r.n > 0) {
             ops_words += (r.m + r.n + 15) / 16;
             max_n = std::max(max_n, r.n);
-            PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = words; j.t_off = r.t_off; j.n = r.n; j.flag = (int)i;
-            ctx->h_peqjobs.push_back(j);
             words += (i64)kPeqStride * r.nbp;
             cells += (i64)r.m * r.n;
         }
@@ -207,8 +226,7 @@ int finish_upload(qb200_ctx *ctx)
     CK(ctx->d_pairs.reserve(sizeof(PairRec) * (size_t)std::max<i64>(n, 1)));
     CK(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairRec) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += (i64)sizeof(PairRec) * n;
-    CK(ctx->d_peqjobs.reserve(sizeof(PeqJob) * std::max<size_t>(ctx->h_peqjobs.size(), 1)));
-    CK(cudaMemcpyAsync(ctx->d_peqjobs.p, ctx->h_peqjobs.data(), sizeof(PeqJob) * ctx->h_peqjobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->d_peqjobs.reserve(sizeof(PeqJob) * (size_t)std::max<i64>(n, 1)));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ran = false;
     return 0;
@@ -382,6 +400,8 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    ctx->h_pairs.release();
+    ctx->h_stage.release();
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -421,12 +441,13 @@ int qb200_upload(qb200_ctx_t *ctx, const qb200_batch_t *b)
     CK(cudaSetDevice(ctx->device));
     ctx->n_pairs = b->n_pairs; ctx->raw_bytes = b->seqs_bytes; ctx->d_raw_ext = nullptr;
     memset(&ctx->stats, 0, sizeof ctx->stats);
-    int rc = build_pair_records(ctx, b->n_pairs, b->pattern_off, b->pattern_len, b->text_off, b->text_len, b->seqs_bytes);
-    if (rc) return rc;
+    // the characters go first: from pinned memory the copy runs while the host builds the pair records below
     const size_t padded = ((size_t)b->seqs_bytes + 15) / 16 * 16 + 32;
     CK(ctx->d_raw.reserve(padded));
     CK(cudaMemsetAsync(ctx->d_raw.as<char>() + (padded - 48), 0, 48, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_raw.p, b->seqs, (size_t)b->seqs_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = build_pair_records(ctx, b->n_pairs, b->pattern_off, b->pattern_len, b->text_off, b->text_len, b->seqs_bytes);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
     ctx->stats.h2d_bytes += b->seqs_bytes;
     return finish_upload(ctx);
 }
@@ -454,10 +475,25 @@ int qb200_upload_device(qb200_ctx_t *ctx, const qb200_batch_t *b)
 static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std::vector<int> &slow_pairs,
                          i64 &n_leaves_total, i64 &ops_words_total, i64 &range_total, std::vector<PairLeaves> &slow_pl);
 
+// QB200_TRACE=2: wall-clock checkpoints inside qb200_run (host-side stalls do not show in the CUDA-event stage times)
+struct RunTrace {
+    bool on; std::chrono::steady_clock::time_point t0, last;
+    RunTrace() : on(getenv("QB200_TRACE") && atoi(getenv("QB200_TRACE")) >= 2), t0(std::chrono::steady_clock::now()), last(t0) {}
+    void pt(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[qb200 run] %-18s +%8.3f ms (%.3f)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
+
 int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
 {
     if (!ctx || !params) return QB200_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    RunTrace rt;
     const quicked_params_t prm = *params;
     const i64 n = ctx->n_pairs;
     const i64 h2d = ctx->stats.h2d_bytes;
@@ -493,6 +529,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     CK(ctx->d_list_slow.reserve((size_t)n * 4));
     if (!ctx->h_pinned) CK(cudaHostAlloc(&ctx->h_pinned, 4096, cudaHostAllocDefault));
 
+    rt.pt("buffers");
     // ---- prepare: codes + forward match masks ----
     {
         Span sp(ctx, ST_PREP);
@@ -509,9 +546,9 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         }
         CK(ctx->d_peq.reserve((size_t)ctx->peq_words * 8 + 64));
         CK(ctx->d_pairodd.reserve((size_t)n + 16));
-        CK(cudaMemsetAsync(ctx->d_pairodd.p, 1, (size_t)n + 16, ctx->stream));      // pairs without a job (an empty side) never reach the kernels
-        const int nj = (int)ctx->h_peqjobs.size();
+        const int nj = ni;                                  // one forward-pattern job per pair, made on the device
         if (nj) {
+            k_make_peqjobs<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_peqjobs.as<PeqJob>());
             k_build_peq<<<(nj + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_peqjobs.as<PeqJob>(), nj, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
                                                                ctx->d_pairodd.as<unsigned char>());
             CK(cudaGetLastError());
@@ -519,6 +556,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         }
     }
 
+    rt.pt("prepare launched");
     // ---- QUICKED fast path: one fused kernel (WindowEd(S) -> BandEd fill -> traceback) for narrow-band pairs ----
     // Measured on B200 (profiles/README.md): the fused kernel wins on small, launch-bound jobs (100 bp x 100 k pairs:
     // 0.70 vs 1.09 ms) and needs no 48 GB traceback pool; on big batches three specialised kernels are ~10 % faster.
@@ -591,6 +629,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         ctx->stats.kernel_launches++;
     }
 
+    rt.pt("ws launched");
     // ---- plan: classify every pair and lay out the pools with one scan ----
     RunPlan plan;
     {
@@ -671,6 +710,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)tot.sc * 4, ctx->stream));
     }
 
+    rt.pt("plan synced");
     // ---- fast path: fill + traceback, chunked only if the traceback state exceeds the pool ----
     if (tot.leaf > 0) {
         size_t free_b = 0, total_b = 0;
@@ -725,6 +765,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         ctx->stats.leaves += tot.leaf;
     }
 
+    rt.pt("fill+trace launched");
     // ---- slow path ----
     if (tot.slow > 0) {
         int rc = run_slow_path(ctx, prm, slow_pairs, n_leaves, ops_words, range_ints, slow_pl);
@@ -770,12 +811,17 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
             ctx->have_cigar = true;
         }
     }
+    rt.pt("text launched");
     CK(cudaEventRecord(ev_end, ctx->stream));
+    // word-step counters: through the pinned scratch on this stream (a synchronous cudaMemcpy on the legacy stream
+    // queued behind the other pipeline workers' copies: 3 ms per call)
+    CK(cudaMemcpyAsync(ctx->h_pinned + 64, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    rt.pt("final sync");
 
     // ---- stats ----
     u64 counters[4];
-    CK(cudaMemcpy(counters, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost));
+    memcpy(counters, ctx->h_pinned + 64, 32);
     ctx->stats.word_steps_windowed = (i64)counters[0];
     ctx->stats.word_steps_banded = (i64)counters[1];
     ctx->stats.word_steps = (i64)(counters[0] + counters[1]);
@@ -1275,23 +1321,48 @@ int qb200_download(qb200_ctx_t *ctx, qb200_results_t *res)
         return 0;
     }
     if (n == 0) { if (res->cigar_off) res->cigar_off[0] = 0; return 0; }
-    if (res->score) CK(cudaMemcpyAsync(res->score, ctx->d_score.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (res->status) CK(cudaMemcpyAsync(res->status, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.d2h_bytes += n * 8;
+    // Device-to-host copies into pageable memory are staged by the driver under a lock that also stalls the other
+    // pipeline workers' launches, so everything goes through page-locked memory: the caller's buffer when it is
+    // (qb200_host_alloc / cudaHostRegister), this context's staging buffer otherwise.
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool with_cigar = ctx->have_cigar && res->cigar_off;
     int rc = 0;
-    if (ctx->have_cigar && res->cigar_off) {
-        CK(cudaMemcpyAsync(res->cigar_off, ctx->d_cigoff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->stats.d2h_bytes += (n + 1) * 8;
+    if (with_cigar) {
         res->cigar_bytes = ctx->cigar_total;
         if (!res->cigar || res->cigar_capacity < ctx->cigar_total) rc = QB200_ERR_CAPACITY;
-        else {
-            CK(cudaMemcpyAsync(res->cigar, ctx->d_cigar.p, (size_t)ctx->cigar_total, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    const bool copy_text = with_cigar && rc == 0 && ctx->cigar_total > 0;
+    const bool stage_text = copy_text && !pinned(res->cigar);
+    const size_t small = (size_t)n * 8 + (size_t)(n + 1) * 8;
+    if (!ctx->h_stage.resize(small + (stage_text ? (size_t)ctx->cigar_total : 0))) { ctx->err = "out of pinned host memory"; return QB200_ERR_OOM; }
+    unsigned char *st = ctx->h_stage.data();
+    int32_t *st_score = reinterpret_cast<int32_t *>(st), *st_status = st_score + n;
+    int64_t *st_off = reinterpret_cast<int64_t *>(st + (size_t)n * 8);
+    if (res->score) CK(cudaMemcpyAsync(st_score, ctx->d_score.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (res->status) CK(cudaMemcpyAsync(st_status, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += n * 8;
+    if (with_cigar) {
+        CK(cudaMemcpyAsync(st_off, ctx->d_cigoff.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->stats.d2h_bytes += (n + 1) * 8;
+        if (copy_text) {
+            CK(cudaMemcpyAsync(stage_text ? reinterpret_cast<char *>(st + small) : res->cigar, ctx->d_cigar.p, (size_t)ctx->cigar_total,
+                               cudaMemcpyDeviceToHost, ctx->stream));
             ctx->stats.d2h_bytes += ctx->cigar_total;
         }
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (res->score) memcpy(res->score, st_score, (size_t)n * 4);
+    if (res->status) memcpy(res->status, st_status, (size_t)n * 4);
+    if (with_cigar) {
+        memcpy(res->cigar_off, st_off, (size_t)(n + 1) * 8);
+        if (stage_text) memcpy(res->cigar, st + small, (size_t)ctx->cigar_total);
     } else if (res->cigar_off) {
         for (i64 i = 0; i <= n; ++i) res->cigar_off[i] = 0;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
     return rc;
 }
 

@@ -38,6 +38,17 @@ struct PeqJob {
     int flag = -1; // index into the per-pair "odd characters" flags, -1: none wanted
 };
 
+// The forward-pattern job of every pair of a batch, derived on the device from its PairRec (nothing to upload).
+__global__ void __launch_bounds__(256) k_make_peqjobs(const PairRec *__restrict__ pairs, int n, PeqJob *__restrict__ jobs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PairRec r = pairs[i];
+    PeqJob j;
+    j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = r.peq_off; j.t_off = r.t_off; j.n = r.n; j.flag = i;
+    jobs[i] = j;
+}
+
 // One warp per table.  Each iteration covers one 64-row block: two coalesced 32-byte reads of codes, five ballots
 // each.  Rows >= m inside the last block match every code (reference bpm_banded.c:77-86); the two extra blocks are 0.
 // With job.flag >= 0 the warp also reports whether the pattern or the text holds a character outside "ACGTN" (the
@@ -50,6 +61,10 @@ __global__ void __launch_bounds__(256) k_build_peq(const PeqJob *__restrict__ jo
     const int lane = threadIdx.x & 31;
     if (warp >= n_jobs) return;
     const PeqJob job = jobs[warp];
+    if (job.m <= 0 || (job.flag >= 0 && job.n <= 0)) {        // a pair with an empty side has no table (and no space for one)
+        if (job.flag >= 0 && lane == 0) odd_flags[job.flag] = 1;
+        return;
+    }
     const int nblk = (job.m + 63) >> 6, nbp = nblk + 2;
     u64 *dst = peq + job.peq_off;
     u32 any_odd = 0;

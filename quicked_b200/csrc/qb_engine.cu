@@ -1425,8 +1425,10 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
     i64 sub = (i64)sms * kWsResidentCtas * kWsThreads * 2;
     if (const char *e = getenv("QB200_SUB_PAIRS")) sub = std::max<i64>(1024, atoll(e));
     const int S = (int)((n + sub - 1) / sub);
-    int NW = 3;                                               // ring slots
-    if (const char *e = getenv("QB200_WORKERS")) NW = std::max(2, std::min(atoi(e), (int)qb200_ctx::kWorkers));
+    int NC = 2;                                               // compute threads: two sub-batches' kernels interleave on the
+    if (const char *e = getenv("QB200_COMPUTE_THREADS")) NC = std::max(1, std::min(atoi(e), 4));   // GPU and fill each other's sync gaps
+    int NW = NC + 2;                                          // ring slots: one uploading, NC computing, one downloading
+    if (const char *e = getenv("QB200_WORKERS")) NW = std::max(NC + 1, std::min(atoi(e), (int)qb200_ctx::kWorkers));
     const bool trace = getenv("QB200_TRACE") != nullptr;
     for (int k = 0; k < NW; ++k) {
         if (!ctx->child[k]) {
@@ -1480,9 +1482,9 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
             cv.notify_all();
         }
     });
-    std::thread computer([&] {
+    auto compute_loop = [&](int tid) {
         cudaSetDevice(ctx->device);
-        for (int k = 0; k < S; ++k) {
+        for (int k = tid; k < S; k += NC) {
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return failed || k < uploaded; });
@@ -1495,13 +1497,17 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
             if (trace) fprintf(stderr, "[qb200 pipeline] sub %d computed in %.2f ms (gpu %.2f: prep %.2f ws %.2f fused %.2f fill %.2f trace %.2f cigar %.2f)\n", k, t_ms(t0), c->stats.ms_total,
                                c->stats.ms_prepare, c->stats.ms_windowed_s, c->stats.ms_fused, c->stats.ms_align_fill, c->stats.ms_align_trace, c->stats.ms_cigar);
             {
-                std::lock_guard<std::mutex> lk(mu);
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || computed == k; });              // publish in order: text offsets are cumulative
+                if (failed) return;
                 text_base[(size_t)k + 1] = text_base[(size_t)k] + ((want_cigar && c->have_cigar) ? c->cigar_total : 0);
                 computed = k + 1;
             }
             cv.notify_all();
         }
-    });
+    };
+    std::vector<std::thread> computers;
+    for (int t = 0; t < NC; ++t) computers.emplace_back(compute_loop, t);
     std::thread downloader([&] {
         cudaSetDevice(ctx->device);
         std::vector<int64_t> loc_off;
@@ -1541,7 +1547,9 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
             cv.notify_all();
         }
     });
-    uploader.join(); computer.join(); downloader.join();
+    uploader.join();
+    for (auto &t : computers) t.join();
+    downloader.join();
     if (failed) return failed;
     const i64 total = text_base[(size_t)S];
     if (res->cigar_off) res->cigar_off[n] = want_cigar ? total : 0;

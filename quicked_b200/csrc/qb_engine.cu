@@ -559,8 +559,9 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     rt.pt("prepare launched");
     // ---- QUICKED fast path: one fused kernel (WindowEd(S) -> BandEd fill -> traceback) for narrow-band pairs ----
     // Measured on B200 (profiles/README.md): the fused kernel wins on small, launch-bound jobs (100 bp x 100 k pairs:
-    // 0.70 vs 1.09 ms) and needs no 48 GB traceback pool; on big batches three specialised kernels are ~10 % faster.
-    bool use_fused = (prm.algo == QUICKED) && ctx->raw_bytes < ((i64)64 << 20);
+    // 0.70 vs 1.09 ms) and needs no 48 GB traceback pool; on big batches three specialised kernels are ~10 % faster,
+    // and so they are on small batches of long reads (15 k pairs of 1 kbp: 4.1 ms fused vs ~2.5 ms).
+    bool use_fused = (prm.algo == QUICKED) && ctx->raw_bytes < ((i64)64 << 20) && ctx->max_n <= 300;
     if (const char *e = getenv("QB200_FUSED")) use_fused = (prm.algo == QUICKED) && atoi(e) != 0;
     i64 leaf_base = 0, ops_base = 0;
     if (use_fused) {
@@ -1424,7 +1425,20 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     i64 sub = (i64)sms * kWsResidentCtas * kWsThreads * 2;
     if (const char *e = getenv("QB200_SUB_PAIRS")) sub = std::max<i64>(1024, atoll(e));
-    const int S = (int)((n + sub - 1) / sub);
+    // Sub-batch boundaries: full-size sub-batches in the middle, a ramp of smaller ones at both ends so that the
+    // first upload (nothing to overlap with) and the last compute + download (nothing left to overlap) are short.
+    std::vector<i64> cut{0};
+    {
+        const bool ramp = !getenv("QB200_NO_RAMP") && n >= 4 * sub;
+        const i64 head[2] = {sub / 4, sub / 2}, tail[2] = {sub / 2, sub / 4};
+        i64 tail_total = ramp ? tail[0] + tail[1] : 0;
+        if (ramp) for (i64 h : head) cut.push_back(cut.back() + h);
+        const i64 mid = n - tail_total - cut.back();                      // split evenly: no tiny remainder sub-batch
+        const i64 parts = std::max<i64>(1, (mid + sub - 1) / sub), base0 = cut.back();
+        for (i64 q = 1; q <= parts && mid > 0; ++q) cut.push_back(base0 + mid * q / parts);
+        if (ramp) for (i64 t : tail) cut.push_back(cut.back() + t);
+    }
+    const int S = (int)cut.size() - 1;
     int NC = 2;                                               // compute threads: two sub-batches' kernels interleave on the
     if (const char *e = getenv("QB200_COMPUTE_THREADS")) NC = std::max(1, std::min(atoi(e), 4));   // GPU and fill each other's sync gaps
     int NW = NC + 2;                                          // ring slots: one uploading, NC computing, one downloading
@@ -1465,7 +1479,7 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
             }
             const auto t0 = std::chrono::steady_clock::now();
             qb200_ctx *c = ctx->child[k % NW];
-            const i64 i0 = (i64)k * sub, i1 = std::min(n, i0 + sub), cnt = i1 - i0;
+            const i64 i0 = cut[(size_t)k], i1 = cut[(size_t)k + 1], cnt = i1 - i0;
             i64 lo = b->seqs_bytes, hi = 0;                   // byte range of this sub-batch in the caller's packed buffer
             for (i64 i = i0; i < i1; ++i) {
                 lo = std::min<i64>(lo, std::min<i64>(b->pattern_off[i], b->text_off[i]));
@@ -1519,7 +1533,7 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
             }
             const auto t0 = std::chrono::steady_clock::now();
             qb200_ctx *c = ctx->child[k % NW];
-            const i64 i0 = (i64)k * sub, i1 = std::min(n, i0 + sub), cnt = i1 - i0;
+            const i64 i0 = cut[(size_t)k], i1 = cut[(size_t)k + 1], cnt = i1 - i0;
             const i64 base = text_base[(size_t)k], need = text_base[(size_t)k + 1] - base;
             if (res->cigar_off) loc_off.resize((size_t)cnt + 1);
             qb200_results_t sr;

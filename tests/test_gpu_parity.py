@@ -184,10 +184,14 @@ def test_cigars_replay_and_ragged(gpu, oracle):
             assert replay(expand_rle(g[2]), p.decode(), t.decode()) == g[1]
 
 
-def test_pipelined_align_batch_matches_resident_path(gpu):
-    """qb200_align_batch cuts big batches into double-buffered sub-batches; results must be identical and in order"""
+@pytest.mark.parametrize("sub_pairs", ["", "20000"])
+def test_pipelined_align_batch_matches_resident_path(gpu, sub_pairs, monkeypatch):
+    """qb200_align_batch cuts big batches into pipelined sub-batches (with smaller ones at both ends when there are
+    enough of them: sub_pairs=20000); results must be identical and in order"""
     import ctypes as C
     import quicked_b200 as qb
+    if sub_pairs:
+        monkeypatch.setenv("QB200_SUB_PAIRS", sub_pairs)
     n = 230000
     seqs, po, pl, to, tl = qb.generate_pairs_native(5, n, 100, 0.05)
     gpu.upload_arrays(seqs, po, pl, to, tl)

@@ -54,7 +54,7 @@ def generate_c5(base_pairs, seed):
 ALGOS = {"quicked": 0, "windowed": 1, "banded": 2, "hirschberg": 3}
 
 
-def ncu_traffic_bytes(kernel_substr, csv_name="r1_ncu_full_c2_v3_raw.csv"):
+def ncu_traffic_bytes(kernel_substr, csv_name="r1_ncu_full_c2_v6_raw.csv"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel_substr`, from the committed `ncu --set full`
     capture of this same command (profiles/, 1 M pairs of configs[1]); None when the capture is not there."""
     import csv

@@ -119,7 +119,7 @@ struct qb200_ctx {
     DevBuf d_quad;                         // WindowEd(S) quadrant scratch
     DevBuf d_fmat, d_franges, d_done;      // fused fast path: per-resident-warp matrix slots, live ranges, per-pair done flags
     i64 ops_words_fused = 0;               // op words of all pairs (fused-path region of the op pool)
-    int max_n = 0;
+    int max_n = 0, max_m = 0;
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
     static constexpr int kWorkers = 8;
@@ -194,7 +194,7 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
 {
     if (!ctx->h_pairs.resize((size_t)n)) { ctx->err = "out of pinned host memory"; return QB200_ERR_OOM; }
     i64 words = 0, cells = 0, ops_words = 0;
-    int max_n = 0;
+    int max_n = 0, max_m = 0;
     for (i64 i = 0; i < n; ++i) {
         PairRec &r = ctx->h_pairs[(size_t)i];
         r.p_off = poff[i]; r.t_off = toff[i]; r.m = plen[i]; r.n = tlen[i];
@@ -208,7 +208,7 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
         r.ops_off = ops_words;
         if (r.m > 0 && r.n > 0) {
             ops_words += (r.m + r.n + 15) / 16;
-            max_n = std::max(max_n, r.n);
+            max_n = std::max(max_n, r.n); max_m = std::max(max_m, r.m);
             words += (i64)kPeqStride * r.nbp;
             cells += (i64)r.m * r.n;
         }
@@ -216,7 +216,7 @@ int build_pair_records(qb200_ctx *ctx, i64 n, const int64_t *poff, const int32_t
     ctx->peq_words = words;
     ctx->cells = cells;
     ctx->ops_words_fused = ops_words;
-    ctx->max_n = max_n;
+    ctx->max_n = max_n; ctx->max_m = max_m;
     return 0;
 }
 
@@ -320,8 +320,9 @@ int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, 
         ctx->stats.kernel_launches++;
         return 0;
     }
-    if (const char *e = getenv("QB200_TRACE_CARVE")) cudaFuncSetAttribute(k_traceback_thread, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-    k_traceback_thread<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub,
+    auto kern = k_traceback_thread;
+    if (const char *e = getenv("QB200_TRACE_CARVE")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+    kern<<<(n_tasks + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub,
                                                                         ctx->raw(), ctx->d_matrix.as<ulonglong2>(), ctx->d_ranges.as<int2>(),
                                                                         ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>());
     CK(cudaGetLastError());
@@ -534,7 +535,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     {
         Span sp(ctx, ST_PREP);
         const size_t padded = ((size_t)ctx->raw_bytes + 15) / 16 * 16;
-        CK(ctx->d_codes.reserve(padded + 64));            // thread kernels read whole aligned 16-byte chunks, up to 48 B past a text
+        CK(ctx->d_codes.reserve(padded + 128));            // thread kernels read whole aligned 16-byte chunks, up to 48 B past a text
         const i64 nvec = (i64)(padded / 16);
         if (ctx->d_raw_ext && ((uintptr_t)ctx->d_raw_ext & 15)) { ctx->err = "device character buffer must be 16-byte aligned"; return QB200_ERR_ARG; }
         if (ctx->d_raw_ext && (size_t)ctx->raw_bytes != padded) { ctx->err = "device character buffer size must be a multiple of 16"; return QB200_ERR_ARG; }
@@ -546,13 +547,19 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         }
         CK(ctx->d_peq.reserve((size_t)ctx->peq_words * 8 + 64));
         CK(ctx->d_pairodd.reserve((size_t)n + 16));
-        const int nj = ni;                                  // one forward-pattern job per pair, made on the device
-        if (nj) {
-            k_make_peqjobs<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_peqjobs.as<PeqJob>());
-            k_build_peq<<<(nj + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_peqjobs.as<PeqJob>(), nj, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
-                                                               ctx->d_pairodd.as<unsigned char>());
+        // forward match masks (+ the per-pair odd-character flags): one thread per pattern on big batches of short
+        // patterns, one warp per pattern otherwise (job list derived on the device from the pair records)
+        if (ni >= 16384 && ctx->max_m <= 32768 && !getenv("QB200_PEQ_WARP")) {
+            k_build_peq_pairs<<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(),
+                                                                       ctx->d_peq.as<u64>(), ctx->d_pairodd.as<unsigned char>());
             CK(cudaGetLastError());
             ctx->stats.kernel_launches++;
+        } else if (ni) {
+            k_make_peqjobs<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_peqjobs.as<PeqJob>());
+            k_build_peq<<<(ni + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_peqjobs.as<PeqJob>(), ni, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
+                                                               ctx->d_pairodd.as<unsigned char>());
+            CK(cudaGetLastError());
+            ctx->stats.kernel_launches += 2;
         }
     }
 

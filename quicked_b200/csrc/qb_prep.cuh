@@ -109,4 +109,66 @@ __global__ void __launch_bounds__(256) k_build_peq(const PeqJob *__restrict__ jo
     }
 }
 
+// k_build_peq_pairs: the forward-pattern tables of a BIG batch, ONE PATTERN PER THREAD (the warp-per-pattern kernel
+// above spends ~67 thread-instructions per pattern row on ballots and address arithmetic and is ALU-bound: 2.8 ms per
+// 1 M patterns of 1 kbp).  A thread reads its pattern 8 code bytes at a time (aligned loads, realigned with a funnel
+// shift), peels the three code bit planes and the odd-character plane off all 8 bytes with one multiply each
+// (movemask: ((x >> k) & 0x01..01) * 0x0102040810204080 >> 56), and turns the four 64-row planes of a block into the
+// six masks with a few 64-bit logic ops: ~6 instructions per row.  The text is scanned for odd characters on the way.
+__device__ __forceinline__ u32 movemask8(u64 x, int k)     // bit k of each of the 8 bytes of x -> 8 bits
+{
+    return (u32)((((x >> k) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+}
+
+__global__ void __launch_bounds__(128) k_build_peq_pairs(const PairRec *__restrict__ pairs, int n, const unsigned char *__restrict__ codes,
+                                                         u64 *__restrict__ peq, unsigned char *__restrict__ odd_flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PairRec r = pairs[i];
+    if (r.m <= 0 || r.n <= 0) { odd_flags[i] = 1; return; }       // no table (and no space for one)
+    const int nblk = (r.m + 63) >> 6, nbp = nblk + 2;
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(peq + r.peq_off);
+    const unsigned long long p0 = (unsigned long long)(codes + r.p_off);
+    const u64 *src = reinterpret_cast<const u64 *>(p0 & ~7ull);
+    const unsigned sh = 8u * (unsigned)(p0 & 7ull);
+    u64 prev = __ldg(src);
+    u64 any_odd = 0;
+    for (int blk = 0; blk < nblk; ++blk) {
+        u64 b0 = 0, b1 = 0, b2 = 0, od = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const u64 next = __ldg(src + blk * 8 + q + 1);       // reads < 16 B past the pattern: inside the padded buffer
+            const u64 w = sh ? ((prev >> sh) | (next << (64u - sh))) : prev;
+            prev = next;
+            b0 |= (u64)movemask8(w, 0) << (8 * q);
+            b1 |= (u64)movemask8(w, 1) << (8 * q);
+            b2 |= (u64)movemask8(w, 2) << (8 * q);
+            od |= (u64)movemask8(w, 3) << (8 * q);
+        }
+        const int rows = r.m - blk * 64;                          // rows of the pattern in this block (>= 1)
+        const u64 valid = rows >= 64 ? ~0ull : ((1ull << rows) - 1ull), pad = ~valid;   // rows >= m match every code
+        const u64 lo = ~b2 & valid;
+        const u64 e0 = (lo & ~b1 & ~b0) | pad, e1 = (lo & ~b1 & b0) | pad, e2 = (lo & b1 & ~b0) | pad, e3 = (lo & b1 & b0) | pad,
+                  e4 = (b2 & valid) | pad;
+        od &= valid;
+        any_odd |= od;
+        dst[blk * 3 + 0] = make_ulonglong2(e0, e1);
+        dst[blk * 3 + 1] = make_ulonglong2(e2, e3);
+        dst[blk * 3 + 2] = make_ulonglong2(e4, od);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dst[nblk * 3 + k] = make_ulonglong2(0, 0);       // the two blocks past the pattern
+    (void)nbp;
+    // odd characters of the text: aligned 8-byte words, bytes outside the text masked off
+    const unsigned long long t0 = (unsigned long long)(codes + r.t_off), t1 = t0 + (unsigned long long)r.n;
+    for (unsigned long long a = t0 & ~7ull; a < t1; a += 8) {
+        u64 msk = 0x0808080808080808ull;
+        if (a < t0) msk <<= 8 * (unsigned)(t0 - a);
+        if (a + 8 > t1) msk &= 0x0808080808080808ull >> (8 * (unsigned)(a + 8 - t1));
+        any_odd |= __ldg(reinterpret_cast<const u64 *>(a)) & msk;
+    }
+    odd_flags[i] = any_odd ? 1 : 0;
+}
+
 }  // namespace qb

@@ -136,7 +136,9 @@ __device__ __forceinline__ void traceback_walk_thread(int m, int n, i64 cutoff, 
 // Mv[column h]; (Pv,Mv) of one (column, word) is a single 16-byte entry, so the entry fetched for Mv at column h
 // is reused for Pv when the walk moves to column h-1, and the live ranges are cached per 64-column block:
 // about one 16-byte load per visited column instead of four dependent loads per step.
-__global__ void __launch_bounds__(128)
+// 56 registers, 9 CTAs per SM.  Trading registers for occupancy does not pay: 48 / 40 / 32 registers (10 / 12 / 14
+// CTAs) spill the cached entries and take 16 / 29 / 65 ms instead of 10.5 per 1 M pairs of 1 kbp.
+__global__ void __launch_bounds__(128, 9)
 k_traceback_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
                    const unsigned char *__restrict__ raw, const ulonglong2 *__restrict__ matrix,
                    const int2 *__restrict__ range_pool, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)

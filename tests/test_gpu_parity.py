@@ -306,6 +306,30 @@ def test_stage1_bounds_match_oracle(oracle, fused, monkeypatch):
     a.close()
 
 
+def test_big_batch_with_odd_characters(oracle, monkeypatch):
+    """>= 16 384 pairs take the thread-per-pattern match-mask builder and (unfused) the slim WindowEd path; a tenth of
+    the pairs carry lower-case / IUPAC / other bytes, which must switch those pairs to the raw-byte compare"""
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_FUSED", "0")
+    rng = np.random.default_rng(123)
+    pairs = generate_pairs(12000, 150, 0.08, seed=71) + generate_pairs(5000, 400, 0.1, seed=72)
+    pairs = [(p.encode() if isinstance(p, str) else p, t.encode() if isinstance(t, str) else t) for p, t in pairs]
+    for i in rng.choice(len(pairs), size=len(pairs) // 10, replace=False):
+        p, t = bytearray(pairs[i][0]), bytearray(pairs[i][1])
+        for buf in (p, t):
+            for k in rng.integers(0, len(buf), size=6):
+                buf[k] = ord(rng.choice(list(chr(buf[k]).lower() + "NRn*")))
+        pairs[i] = (bytes(p), bytes(t))
+    a = qb.BatchAligner(device=0)
+    got = a.align(pairs, algo=0)
+    bound, hew = a.bounds()
+    for i, ((p, t), g) in enumerate(zip(pairs, got)):
+        assert g == oracle.align(p, t, algo=0), i
+    for i in rng.choice(len(pairs), size=1500, replace=False):
+        assert (int(bound[i]), int(hew[i])) == oracle.windowed_score(pairs[i][0], pairs[i][1], 2, 1, 40, True), i
+    a.close()
+
+
 def test_edge_cases_match_oracle(gpu, oracle):
     """empty batch, single characters, identical / unrelated sequences, all-N, very unequal lengths, lowercase"""
     assert gpu.align([]) == []

@@ -110,6 +110,14 @@ int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, dou
                              char *seqs, int64_t *pattern_off, int32_t *pattern_len,
                              int64_t *text_off, int32_t *text_len);
 
+/* --- SAM-style CIGAR of one alignment (host-side string transform; reference cigar_compute_CIGAR /
+ * cigar_sprint_SAM_CIGAR, quicked_utils/src/cigar.c:193-240, :504-529).  `cigar` is the run-length text this library
+ * and the reference's quicked_align produce ("12M1X3I...": M match, X mismatch, I consumes a text character,
+ * D a pattern character).  show_mismatches != 0: matches print as '=', mismatches as 'X'; == 0: both merge into 'M'
+ * — except that, like the reference, the very first operation is taken as it is (an alignment that starts with a
+ * mismatch begins "1X").  Returns the length written (NUL-terminated), or -(bytes needed) if `capacity` is too small. */
+int64_t qb200_cigar_to_sam(const char *cigar, int show_mismatches, char *out, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ QB200_ERR_NO_DEVICE, QB200_ERR_CUDA, QB200_ERR_ARG, QB200_ERR_OOM, QB200_ERR_CAP
 EXPORTS = ["quicked_check_error", "quicked_status_msg", "quicked_default_params", "quicked_new", "quicked_free",
            "quicked_align", "qb200_device_count", "qb200_create", "qb200_destroy", "qb200_set_stream",
            "qb200_set_workspace_limit", "qb200_last_error", "qb200_upload", "qb200_upload_device", "qb200_run",
-           "qb200_download", "qb200_get_stats", "qb200_get_bounds", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
+           "qb200_download", "qb200_get_stats", "qb200_get_bounds", "qb200_cigar_to_sam", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
            "qb200_generate_pairs", "qb200_measure_int_peak"]
 
 
@@ -96,6 +96,8 @@ def load():
     L.qb200_download.argtypes = [C.c_void_p, C.POINTER(Results)]
     L.qb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.qb200_get_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.qb200_cigar_to_sam.restype = C.c_int64
+    L.qb200_cigar_to_sam.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
     L.qb200_align_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Batch), C.POINTER(Results)]
     L.qb200_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qb200_host_alloc.restype = C.c_void_p
@@ -281,6 +283,18 @@ class BatchAligner:
                 c = raw[off[i]:off[i + 1] - 1].decode()
             out.append((int(status[i]), int(score[i]), c))
         return out
+
+
+def cigar_to_sam(cigar, show_mismatches=False):
+    """SAM-style CIGAR of one alignment (reference cigar_sprint_SAM_CIGAR)"""
+    lib = load()
+    c = cigar.encode() if isinstance(cigar, str) else cigar
+    buf = C.create_string_buffer(len(c) + 16)
+    n = lib.qb200_cigar_to_sam(c, int(bool(show_mismatches)), buf, len(buf))
+    if n < 0:
+        buf = C.create_string_buffer(-n)
+        n = lib.qb200_cigar_to_sam(c, int(bool(show_mismatches)), buf, len(buf))
+    return buf.raw[:n].decode()
 
 
 def generate_pairs_native(seed, n_pairs, length, error):

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -160,6 +161,49 @@ static inline uint64_t splitmix64(uint64_t &x)
     return z ^ (z >> 31);
 }
 static inline uint32_t rand_below(uint64_t &s, uint32_t n) { return (uint32_t)(((splitmix64(s) >> 32) * (uint64_t)n) >> 32); }
+
+// SAM-style CIGAR (reference cigar.c:193-240): the reference groups the one-character-per-op buffer after mapping
+// X -> M (unless show_mismatches), but never maps the FIRST operation; matches print as '=' with show_mismatches.
+int64_t qb200_cigar_to_sam(const char *cigar, int show_mismatches, char *out, int64_t capacity)
+{
+    if (!cigar || (!out && capacity > 0)) return 0;
+    std::string res;
+    char last_op = 0;
+    long long last_len = 0;
+    bool first = true;
+    auto dump = [&]() {
+        if (!last_len) return;
+        char c = last_op;
+        if (show_mismatches && c == 'M') c = '=';
+        else if (c != 'M' && c != 'I' && c != 'D' && c != 'N' && c != '=' && c != 'X') c = '?';
+        res += std::to_string(last_len);
+        res += c;
+    };
+    auto feed = [&](char op, long long len) {            // len operations `op`, already mapped
+        if (!len) return;
+        if (op == last_op) { last_len += len; return; }
+        dump();
+        last_op = op; last_len = len;
+    };
+    for (const char *p = cigar; *p;) {
+        long long len = 0;
+        while (*p >= '0' && *p <= '9') { len = len * 10 + (*p - '0'); ++p; }
+        if (!*p) break;
+        const char op = *p++;
+        if (len <= 0) continue;
+        const char mapped = (!show_mismatches && op == 'X') ? 'M' : op;
+        if (first) {                                      // operations[begin_offset] is used unmapped (cigar.c:209)
+            first = false;
+            last_op = op; last_len = 1;
+            feed(mapped, len - 1);
+        } else feed(mapped, len);
+    }
+    dump();
+    const int64_t need = (int64_t)res.size() + 1;
+    if (need > capacity) return -need;
+    memcpy(out, res.c_str(), (size_t)need);
+    return need - 1;
+}
 
 int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, double error, char *seqs,
                              int64_t *pattern_off, int32_t *pattern_len, int64_t *text_off, int32_t *text_len)

@@ -99,3 +99,51 @@ def test_native_generator_model():
     assert (seqs == seqs2).all()
     seqs3, *_ = generate_pairs_native(8, 200, 100, 0.05)
     assert (seqs != seqs3).any()
+
+
+class _RefCigar(C.Structure):      # quicked_utils/include/cigar.h:33-47
+    _fields_ = [("operations", C.c_char_p), ("cigar_buffer", C.POINTER(C.c_uint32)), ("cigar_length", C.c_int),
+                ("max_operations", C.c_int), ("begin_offset", C.c_int), ("end_offset", C.c_int), ("score", C.c_int),
+                ("end_v", C.c_int), ("end_h", C.c_int)]
+
+
+def _expand(cigar):
+    return "".join(op * int(n) for n, op in re.findall(r"(\d+)([MXID])", cigar))
+
+
+SAM_GOLDEN = [("2M1X1M", "4M", "2=1X1="), ("3X2M1I", "1X4M1I", "3X2=1I"), ("1X", "1X", "1X"), ("5M", "5M", "5="),
+              ("1M2X3D4I5M", "3M3D4I5M", "1=2X3D4I5="), ("2D1X1X3M", "2D5M", "2D2X3="), ("", "", "")]
+
+
+def test_cigar_to_sam_golden():
+    """qb200_cigar_to_sam on known answers (the first operation is never mapped: reference cigar.c:209)"""
+    from quicked_b200.capi import cigar_to_sam
+    for cig, plain, shown in SAM_GOLDEN:
+        assert cigar_to_sam(cig, False) == plain
+        assert cigar_to_sam(cig, True) == shown
+
+
+def test_cigar_to_sam_matches_reference(reference):
+    """against the unmodified reference's cigar_sprint_SAM_CIGAR (quicked_utils/src/cigar.c:504-529) on random CIGARs"""
+    import numpy as np
+    from quicked_b200.capi import cigar_to_sam
+    ref = reference.lib
+    ref.cigar_sprint_SAM_CIGAR.restype = C.c_int
+    ref.cigar_sprint_SAM_CIGAR.argtypes = [C.c_char_p, C.c_int, C.POINTER(_RefCigar), C.c_bool]
+    rng = np.random.default_rng(5)
+    cases = [c for c, _, _ in SAM_GOLDEN if c]
+    for _ in range(300):
+        runs, last = [], ""
+        for _ in range(int(rng.integers(1, 40))):
+            op = str(rng.choice([o for o in "MMMXID" if o != last]))
+            runs.append(f"{int(rng.integers(1, 30))}{op}")
+            last = op
+        cases.append("".join(runs))
+    for cig in cases:
+        ops = _expand(cig).encode()
+        for show in (False, True):
+            buf32 = (C.c_uint32 * (len(ops) + 1))()
+            rc = _RefCigar(ops, buf32, 0, len(ops), 0, len(ops), 0, 0, 0)
+            out = C.create_string_buffer(2 * len(ops) + 16)
+            n = ref.cigar_sprint_SAM_CIGAR(out, len(out), C.byref(rc), show)
+            assert cigar_to_sam(cig, show) == out.raw[:n].decode(), (cig, show)

@@ -232,6 +232,45 @@ def test_cli_matches_oracle_output_format(gpu, oracle, tmp_path):
             assert line == f"{sc}\t{cg}", (algo, line[:60])
 
 
+def test_cli_streaming_fasta_in_sam_out(gpu, oracle, tmp_path):
+    """FASTA records (multi-line, consecutive records = pattern, text) streamed in small batches, SAM
+    lines out with the reference's SAM CIGAR (query = text, reference = pattern) and NM = score; the plain
+    `score<TAB>CIGAR` output of the same run must equal the .seq run's"""
+    import subprocess
+    from quicked_b200.capi import cigar_to_sam
+    from _common import ROOT
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=True)
+    pairs = [(p.decode(), t.decode()) for p, t in generate_pairs(500, 300, 0.1, seed=31) + generate_pairs(10, 4000, 0.15, seed=32)]
+    pairs.append(("ACGT", ""))
+    fa = tmp_path / "in.fa"
+    with open(fa, "w") as f:
+        for i, (p, t) in enumerate(pairs):
+            for name, sq in ((f"p{i} some description", p), (f"t{i}", t)):
+                f.write(f">{name}\n")
+                for k in range(0, len(sq), 70):
+                    f.write(sq[k:k + 70] + "\n")
+    exe = os.path.join(ROOT, "tools", "qb_align_benchmark")
+    for eqx in (False, True):
+        out, sam = tmp_path / "fa.out", tmp_path / "fa.sam"
+        r = subprocess.run([exe, "-a", "quicked", "-i", str(fa), "-o", str(out), "--output-sam", str(sam), "--batch-size", "97",
+                            "--check", "correct"] + (["--sam-eqx"] if eqx else []), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        lines = out.read_text().splitlines()
+        sam_lines = [l for l in sam.read_text().splitlines() if not l.startswith("@")]
+        assert len(lines) == len(pairs) and len(sam_lines) == len(pairs)
+        for i, ((p, t), line, sl) in enumerate(zip(pairs, lines, sam_lines)):
+            st, sc, cg = oracle.align(p, t, algo=0)
+            f = sl.split("\t")
+            if st < -2:                                    # empty sequence: ERROR line / unmapped SAM record
+                assert line.startswith("ERROR") and f[1] == "4"
+                continue
+            assert line == f"{sc}\t{cg}"
+            assert f[0] == f"t{i}" and f[2] == f"p{i}" and f[1] == "0" and f[3] == "1"
+            assert f[5] == cigar_to_sam(cg, eqx) and f[9] == t and f[-1] == f"NM:i:{sc}"
+            qlen = sum(int(n) for n, op in __import__("re").findall(r"(\d+)([MIDX=])", f[5]) if op in "MIX=")
+            assert qlen == len(t)                          # SAM: query-consuming ops cover SEQ
+
+
 def test_cpp_binding_example(tmp_path):
     """include/quicked.hpp: the reference's C++ binding surface (bindings/cpp/quicked.hpp:46-73) + alignMany"""
     import subprocess

@@ -9,20 +9,28 @@
 //
 // The reference's OpenMP batch loop (align_benchmark.c:232-306) is replaced by one qb200_align_batch() per batch.
 // --check correct replays every CIGAR on its pair (cigar_check_alignment semantics, cigar.c:363-434).
+//
+// Streaming: a reader thread parses batch k+1 into page-locked buffers (`.seq` pairs or FASTA
+// records, consecutive records = pattern, text) while the GPU aligns batch k and a writer thread formats batch k-1;
+// --output-sam writes one SAM line per pair (query = text, reference = pattern, CIGAR through qb200_cigar_to_sam,
+// the reference's cigar_sprint_SAM_CIGAR, cigar.c:504-529).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <getopt.h>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "quicked_b200.h"
 
 struct Options {
-    std::string algo = "quicked", input, output;
-    bool output_full = false, force_scalar = false, check = false, only_score = false;
+    std::string algo = "quicked", input, output, output_sam, input_format = "auto";
+    bool output_full = false, force_scalar = false, check = false, only_score = false, sam_eqx = false;
     int bandwidth = 15, window_size = 9, overlap_size = 1, hew_threshold = 40, hew_percentage = 15;
     long batch_size = 1000000;
     int device = 0, verbose = 0;
@@ -36,9 +44,11 @@ static void usage()
             "        [Algorithm]\n"
             "          --algorithm|a ALGORITHM   quicked | edit-banded | edit-windowed | edit-banded-hirschberg\n"
             "        [Input & Output]\n"
-            "          --input|i PATH            '>pattern' / '<text' line pairs\n"
+            "          --input|i PATH            '>pattern' / '<text' line pairs, or FASTA (records 2i, 2i+1 = pattern, text)\n"
+            "          --input-format FMT        auto | seq | fasta\n"
             "          --output|o PATH           score<TAB>CIGAR per pair\n"
             "          --output-full PATH        lengths, score, sequences, CIGAR\n"
+            "          --output-sam PATH         one SAM line per pair (query = text, reference = pattern); --sam-eqx: =/X ops\n"
             "        [Other Parameters]\n"
             "          --bandwidth INT  --window-size INT  --overlap-size INT\n"
             "          --hew-threshold INT  --hew-percentage INT  --force-scalar  --only-score\n"
@@ -67,12 +77,103 @@ static bool replay_ok(const char *cigar, const char *p, int m, const char *t, in
     return i == m && j == n && cost == score;
 }
 
+// Growable page-locked byte buffer (contents kept across growth).
+struct PinnedBytes {
+    char *p = nullptr;
+    size_t cap = 0, n = 0;
+    void reserve(size_t want)
+    {
+        if (want <= cap) return;
+        size_t nc = std::max(want, cap + cap / 2 + (size_t)(1 << 20));
+        char *q = (char *)qb200_host_alloc(nc);
+        if (!q) { fprintf(stderr, "qb_align_benchmark: out of page-locked memory\n"); exit(3); }
+        if (p) { memcpy(q, p, n); qb200_host_free(p); }
+        p = q; cap = nc;
+    }
+    void append(const char *src, size_t len) { reserve(n + len + 1); memcpy(p + n, src, len); n += len; }
+    ~PinnedBytes() { if (p) qb200_host_free(p); }
+};
+
+struct Batch {
+    PinnedBytes seqs, cig;
+    std::vector<int64_t> po, to, coff;
+    std::vector<int32_t> pl, tl, score, status;
+    std::vector<std::string> pname, tname;      // FASTA record names (empty for .seq input)
+    int64_t first_index = 0;
+    int state = 0;                              // 0 free, 1 parsed, 2 aligned
+    bool last = false;
+    void clear() { seqs.n = 0; po.clear(); to.clear(); pl.clear(); tl.clear(); pname.clear(); tname.clear(); last = false; }
+    void add(const char *p, long m, const char *t, long n)
+    {
+        po.push_back((int64_t)seqs.n); pl.push_back((int32_t)std::max(m, 0L)); seqs.append(p, (size_t)std::max(m, 0L));
+        to.push_back((int64_t)seqs.n); tl.push_back((int32_t)std::max(n, 0L)); seqs.append(t, (size_t)std::max(n, 0L));
+    }
+};
+
+// Input: `.seq` ('>pattern' / '<text' lines, align_benchmark.c:73-99) or FASTA (multi-line records; consecutive
+// records form a pair).  next() appends one pair to the batch; false at end of input.
+struct PairReader {
+    FILE *in; bool fasta = false;
+    char *l1 = nullptr, *l2 = nullptr; size_t a1 = 0, a2 = 0;
+    std::string pending_header, seq_a, seq_b, name_a, name_b;
+    PairReader(FILE *f, const std::string &fmt) : in(f)
+    {
+        if (fmt == "fasta") fasta = true;
+        else if (fmt == "auto") {                        // FASTA iff the second line does not start with '<' or '>'
+            const long pos = ftell(in);
+            ssize_t n1 = getline(&l1, &a1, in), n2 = getline(&l2, &a2, in);
+            fasta = n1 > 0 && n2 > 0 && l1[0] == '>' && l2[0] != '<' && l2[0] != '>';
+            fseek(in, pos, SEEK_SET);
+        }
+    }
+    ~PairReader() { free(l1); free(l2); }
+    static std::string name_of(const char *line) { const char *e = line; while (*e && *e != ' ' && *e != '\t' && *e != '\n' && *e != '\r') ++e; return std::string(line, e); }
+    bool fasta_record(std::string &name, std::string &seq)
+    {
+        seq.clear();
+        if (pending_header.empty()) {
+            ssize_t n;
+            while ((n = getline(&l1, &a1, in)) >= 0) if (l1[0] == '>') { pending_header = name_of(l1 + 1); if (pending_header.empty()) pending_header = "*"; break; }
+            if (pending_header.empty()) return false;
+        }
+        name = pending_header; pending_header.clear();
+        ssize_t n;
+        while ((n = getline(&l1, &a1, in)) >= 0) {
+            if (l1[0] == '>') { pending_header = name_of(l1 + 1); if (pending_header.empty()) pending_header = "*"; break; }
+            while (n > 0 && (l1[n - 1] == '\n' || l1[n - 1] == '\r' || l1[n - 1] == ' ')) --n;
+            seq.append(l1, (size_t)n);
+        }
+        return true;
+    }
+    bool next(Batch &b)
+    {
+        if (fasta) {
+            if (!fasta_record(name_a, seq_a) || !fasta_record(name_b, seq_b)) return false;
+            b.add(seq_a.data(), (long)seq_a.size(), seq_b.data(), (long)seq_b.size());
+            b.pname.push_back(name_a); b.tname.push_back(name_b);
+            return true;
+        }
+        ssize_t n1 = getline(&l1, &a1, in);
+        if (n1 < 0) return false;
+        ssize_t n2 = getline(&l2, &a2, in);
+        if (n2 < 0) return false;
+        while (n1 > 0 && (l1[n1 - 1] == '\n' || l1[n1 - 1] == '\r')) --n1;
+        while (n2 > 0 && (l2[n2 - 1] == '\n' || l2[n2 - 1] == '\r')) --n2;
+        const char *p = l1 + 1, *t = l2 + 1;
+        long m = n1 - 1, n = n2 - 1;
+        if (l1[0] == '<' && l2[0] == '>') { std::swap(p, t); std::swap(m, n); }   // generate_dataset.c:396-405 prints either order
+        b.add(p, m, t, n);
+        return true;
+    }
+};
+
 int main(int argc, char **argv)
 {
     Options o;
     static struct option long_options[] = {
         {"algorithm", required_argument, 0, 'a'}, {"input", required_argument, 0, 'i'}, {"output", required_argument, 0, 'o'},
-        {"output-full", required_argument, 0, 800}, {"bandwidth", required_argument, 0, 2000}, {"window-size", required_argument, 0, 2001},
+        {"output-full", required_argument, 0, 800}, {"output-sam", required_argument, 0, 801}, {"sam-eqx", no_argument, 0, 802},
+        {"input-format", required_argument, 0, 803}, {"bandwidth", required_argument, 0, 2000}, {"window-size", required_argument, 0, 2001},
         {"overlap-size", required_argument, 0, 2002}, {"hew-threshold", required_argument, 0, 2003}, {"hew-percentage", required_argument, 0, 2004},
         {"force-scalar", no_argument, 0, 2005}, {"only-score", no_argument, 0, 2006}, {"check", required_argument, 0, 'c'},
         {"num-threads", required_argument, 0, 't'}, {"batch-size", required_argument, 0, 4000}, {"device", required_argument, 0, 4002},
@@ -85,6 +186,9 @@ int main(int argc, char **argv)
         case 'i': o.input = optarg; break;
         case 'o': o.output = optarg; break;
         case 800: o.output = optarg; o.output_full = true; break;
+        case 801: o.output_sam = optarg; break;
+        case 802: o.sam_eqx = true; break;
+        case 803: o.input_format = optarg; break;
         case 2000: o.bandwidth = atoi(optarg); break;
         case 2001: o.window_size = atoi(optarg); break;
         case 2002: o.overlap_size = atoi(optarg); break;
@@ -107,6 +211,7 @@ int main(int argc, char **argv)
     else if (o.algo == "edit-windowed") prm.algo = WINDOWED;
     else if (o.algo == "edit-banded-hirschberg") prm.algo = HIRSCHBERG;
     else { fprintf(stderr, "Algorithm '%s' not recognized\n", o.algo.c_str()); return 1; }
+    if (o.input_format != "auto" && o.input_format != "seq" && o.input_format != "fasta") { fprintf(stderr, "Input format '%s' not recognized\n", o.input_format.c_str()); return 1; }
     prm.bandwidth = (unsigned)o.bandwidth; prm.window_size = (unsigned)o.window_size; prm.overlap_size = (unsigned)o.overlap_size;
     prm.hew_threshold[0] = prm.hew_threshold[1] = (unsigned)o.hew_threshold;
     prm.hew_percentage[0] = prm.hew_percentage[1] = (unsigned)o.hew_percentage;
@@ -115,75 +220,126 @@ int main(int argc, char **argv)
     FILE *in = fopen(o.input.c_str(), "r");
     if (!in) { fprintf(stderr, "Input file '%s' couldn't be opened\n", o.input.c_str()); return 1; }
     FILE *out = o.output.empty() ? nullptr : fopen(o.output.c_str(), "w");
+    FILE *sam = o.output_sam.empty() ? nullptr : fopen(o.output_sam.c_str(), "w");
     qb200_ctx_t *gpu = nullptr;
     if (qb200_create(&gpu, o.device) != QB200_OK) { fprintf(stderr, "qb_align_benchmark: no CUDA device (there is no CPU fallback)\n"); return 2; }
+    if (sam) fprintf(sam, "@HD\tVN:1.6\tSO:unknown\n@PG\tID:qb_align_benchmark\tPN:qb_align_benchmark\tDS:query=text reference=pattern algorithm=%s\n", o.algo.c_str());
 
-    std::vector<char> seqs;
-    std::vector<int64_t> po, to;
-    std::vector<int32_t> pl, tl, score, status;
-    std::vector<int64_t> coff;
-    std::vector<char> cig;
-    char *l1 = nullptr, *l2 = nullptr;
-    size_t a1 = 0, a2 = 0;
+    // ---- three stages over a ring of three batches: reader thread -> this thread (GPU) -> writer thread ----
+    constexpr int kRing = 3;
+    Batch ring[kRing];
+    std::mutex mu;
+    std::condition_variable cv;
     long total = 0, bad = 0;
     double t_align = 0;
+    int fatal = 0;
     const auto t_begin = std::chrono::steady_clock::now();
-    bool eof = false;
-    while (!eof) {
-        seqs.clear(); po.clear(); to.clear(); pl.clear(); tl.clear();
-        while ((long)po.size() < o.batch_size) {          // align_benchmark.c:73-99: strip the '>' / '<' and the newline
-            ssize_t n1 = getline(&l1, &a1, in);
-            if (n1 < 0) { eof = true; break; }
-            ssize_t n2 = getline(&l2, &a2, in);
-            if (n2 < 0) { eof = true; break; }
-            while (n1 > 0 && (l1[n1 - 1] == '\n' || l1[n1 - 1] == '\r')) --n1;
-            while (n2 > 0 && (l2[n2 - 1] == '\n' || l2[n2 - 1] == '\r')) --n2;
-            const char *p = l1 + 1, *t = l2 + 1;
-            long m = n1 - 1, n = n2 - 1;
-            if (l1[0] == '<' && l2[0] == '>') { std::swap(p, t); std::swap(m, n); }   // generate_dataset.c:396-405 prints either order
-            po.push_back((int64_t)seqs.size()); pl.push_back((int32_t)std::max(m, 0L)); seqs.insert(seqs.end(), p, p + std::max(m, 0L));
-            to.push_back((int64_t)seqs.size()); tl.push_back((int32_t)std::max(n, 0L)); seqs.insert(seqs.end(), t, t + std::max(n, 0L));
+
+    std::thread reader([&] {
+        PairReader pr(in, o.input_format);
+        int64_t index = 0;
+        for (int k = 0;; ++k) {
+            Batch &b = ring[k % kRing];
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return fatal || b.state == 0; }); if (fatal) return; }
+            b.clear();
+            b.first_index = index;
+            bool more = true;
+            while ((long)b.po.size() < o.batch_size && (more = pr.next(b))) {}
+            b.seqs.append("", 0); b.seqs.p[b.seqs.n++] = 0;
+            index += (int64_t)b.po.size();
+            b.last = !more;
+            { std::lock_guard<std::mutex> lk(mu); b.state = 1; }
+            cv.notify_all();
+            if (b.last) return;
         }
-        const int64_t np = (int64_t)po.size();
-        if (!np) break;
-        seqs.push_back(0);
-        score.assign((size_t)np, -1); status.assign((size_t)np, -1); coff.assign((size_t)np + 1, 0);
-        cig.resize(std::max<size_t>(cig.size(), seqs.size() / 2 + 1024));
-        qb200_batch_t b = {seqs.data(), (int64_t)seqs.size(), np, po.data(), pl.data(), to.data(), tl.data()};
-        qb200_results_t r = {score.data(), status.data(), cig.data(), (int64_t)cig.size(), coff.data(), 0};
-        const auto t0 = std::chrono::steady_clock::now();
-        int rc = qb200_align_batch(gpu, &prm, &b, &r);
-        if (rc == QB200_ERR_CAPACITY) {
-            cig.resize((size_t)r.cigar_bytes + 1024);
-            r.cigar = cig.data(); r.cigar_capacity = (int64_t)cig.size();
-            rc = qb200_align_batch(gpu, &prm, &b, &r);
+    });
+    std::thread writer([&] {
+        std::string samcig;
+        for (int k = 0;; ++k) {
+            Batch &b = ring[k % kRing];
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return fatal || b.state == 2; }); if (fatal) return; }
+            const int64_t np = (int64_t)b.po.size();
+            for (int64_t i = 0; i < np; ++i) {
+                const size_t q = (size_t)i;
+                const char *cg = (prm.only_score || b.coff[q + 1] - b.coff[q] <= 1) ? "-" : b.cig.p + b.coff[q];
+                const bool err = quicked_check_error((quicked_status_t)b.status[q]);
+                const char *P = b.seqs.p + b.po[q], *T = b.seqs.p + b.to[q];
+                if (o.check && !err && !prm.only_score && !replay_ok(cg, P, b.pl[q], T, b.tl[q], b.score[q])) ++bad;
+                if (out) {
+                    if (o.output_full) {
+                        fprintf(out, "%d\t%d\t", b.pl[q], b.tl[q]);
+                        if (err) fprintf(out, "ERROR\t"); else fprintf(out, "%d\t", b.score[q]);
+                        fwrite(P, 1, (size_t)b.pl[q], out); fputc('\t', out);
+                        fwrite(T, 1, (size_t)b.tl[q], out);
+                        fprintf(out, "\t%s\n", err ? (prm.only_score ? "-" : "ERROR") : cg);
+                    } else if (err) fprintf(out, "ERROR\t%s\n", prm.only_score ? "-" : "ERROR");
+                    else fprintf(out, "%d\t%s\n", b.score[q], cg);
+                }
+                if (sam) {
+                    const long long id = (long long)(b.first_index + i);
+                    if (b.tname.empty()) fprintf(sam, "text%lld", id); else fputs(b.tname[q].c_str(), sam);
+                    if (err) fputs("\t4\t*\t0\t0\t*", sam);
+                    else {
+                        if (b.pname.empty()) fprintf(sam, "\t0\tpattern%lld\t1\t255\t", id); else fprintf(sam, "\t0\t%s\t1\t255\t", b.pname[q].c_str());
+                        if (prm.only_score || cg[0] == '-') fputc('*', sam);
+                        else {
+                            samcig.resize(strlen(cg) + 16);
+                            int64_t n = qb200_cigar_to_sam(cg, o.sam_eqx, &samcig[0], (int64_t)samcig.size());
+                            if (n < 0) { samcig.resize((size_t)-n); n = qb200_cigar_to_sam(cg, o.sam_eqx, &samcig[0], (int64_t)samcig.size()); }
+                            fwrite(samcig.data(), 1, (size_t)n, sam);
+                        }
+                    }
+                    fputs("\t*\t0\t0\t", sam);
+                    if (b.tl[q]) fwrite(T, 1, (size_t)b.tl[q], sam); else fputc('*', sam);
+                    if (err) fputs("\t*\n", sam); else fprintf(sam, "\t*\tNM:i:%d\n", b.score[q]);
+                }
+            }
+            total += np;
+            const bool last = b.last;
+            { std::lock_guard<std::mutex> lk(mu); b.state = 0; }
+            cv.notify_all();
+            if (last) return;
         }
-        t_align += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        if (rc != QB200_OK) { fprintf(stderr, "qb_align_benchmark: %s (rc=%d)\n", qb200_last_error(gpu), rc); return 3; }
-        for (int64_t i = 0; i < np; ++i) {
-            const char *cg = (prm.only_score || coff[(size_t)i + 1] - coff[(size_t)i] <= 1) ? "-" : cig.data() + coff[(size_t)i];
-            const bool err = quicked_check_error((quicked_status_t)status[(size_t)i]);
-            if (o.check && !err && !prm.only_score &&
-                !replay_ok(cg, seqs.data() + po[(size_t)i], pl[(size_t)i], seqs.data() + to[(size_t)i], tl[(size_t)i], score[(size_t)i])) ++bad;
-            if (!out) continue;
-            if (o.output_full) {
-                fprintf(out, "%d\t%d\t", pl[(size_t)i], tl[(size_t)i]);
-                if (err) fprintf(out, "ERROR\t"); else fprintf(out, "%d\t", score[(size_t)i]);
-                fwrite(seqs.data() + po[(size_t)i], 1, (size_t)pl[(size_t)i], out); fputc('\t', out);
-                fwrite(seqs.data() + to[(size_t)i], 1, (size_t)tl[(size_t)i], out);
-                fprintf(out, "\t%s\n", err ? (prm.only_score ? "-" : "ERROR") : cg);
-            } else if (err) fprintf(out, "ERROR\t%s\n", prm.only_score ? "-" : "ERROR");
-            else fprintf(out, "%d\t%s\n", score[(size_t)i], cg);
+    });
+    for (int k = 0;; ++k) {
+        Batch &b = ring[k % kRing];
+        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return b.state == 1; }); }
+        const int64_t np = (int64_t)b.po.size();
+        int rc = QB200_OK;
+        if (np) {
+            b.score.assign((size_t)np, -1); b.status.assign((size_t)np, -1); b.coff.assign((size_t)np + 1, 0);
+            b.cig.reserve(std::max<size_t>(b.cig.cap, b.seqs.n / 2 + 1024));
+            qb200_batch_t qb = {b.seqs.p, (int64_t)b.seqs.n, np, b.po.data(), b.pl.data(), b.to.data(), b.tl.data()};
+            qb200_results_t r = {b.score.data(), b.status.data(), b.cig.p, (int64_t)b.cig.cap, b.coff.data(), 0};
+            const auto t0 = std::chrono::steady_clock::now();
+            rc = qb200_align_batch(gpu, &prm, &qb, &r);
+            if (rc == QB200_ERR_CAPACITY) {
+                b.cig.n = 0; b.cig.reserve((size_t)r.cigar_bytes + 1024);
+                r.cigar = b.cig.p; r.cigar_capacity = (int64_t)b.cig.cap;
+                rc = qb200_align_batch(gpu, &prm, &qb, &r);
+            }
+            t_align += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         }
-        total += np;
+        if (rc != QB200_OK) {
+            fprintf(stderr, "qb_align_benchmark: %s (rc=%d)\n", qb200_last_error(gpu), rc);
+            { std::lock_guard<std::mutex> lk(mu); fatal = 3; }
+            cv.notify_all();
+            break;
+        }
+        const bool last = b.last;
+        { std::lock_guard<std::mutex> lk(mu); b.state = 2; }
+        cv.notify_all();
+        if (last) break;
     }
+    reader.join(); writer.join();
+    if (fatal) return fatal;
     const double t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     fprintf(stderr, "...processed %ld reads (alignment = %2.3f seq/s)\n", total, t_align > 0 ? total / t_align : 0.0);
     fprintf(stderr, "[Benchmark]\n=> Total.reads            %ld\n=> Time.Benchmark      %9.2f s\n  => Time.Alignment    %9.2f s\n", total, t_total, t_align);
     if (o.check) fprintf(stderr, "[Accuracy]\n => Alignments.Correct  %ld / %ld\n", total - bad, total);
     if (out) fclose(out);
+    if (sam) fclose(sam);
     fclose(in);
-    free(l1); free(l2);
     qb200_destroy(gpu);
     return bad ? 4 : 0;
 }

@@ -369,6 +369,21 @@ def test_big_batch_with_odd_characters(oracle, monkeypatch):
     a.close()
 
 
+def test_small_matrix_pool_chunks_the_batch(oracle, monkeypatch):
+    """qb200_set_workspace_limit below the traceback state of the batch: fill + traceback run chunk by chunk (thread
+    groups, warp leaves and the host-built leaves of the slow path) and give the same answers"""
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_FUSED", "0")
+    pairs = generate_pairs(3000, 600, 0.1, seed=81) + generate_pairs(60, 6000, 0.2, seed=82) + \
+        generate_pairs(20, 3000, 0.05, seed=83, indels=(4, 200))
+    a = qb.BatchAligner(device=0, workspace_limit=48 << 20)        # the batch needs ~200 MB of (Pv,Mv) entries
+    for algo, kw in ((0, {}), (2, dict(bandwidth=20)), (3, dict(bandwidth=20))):
+        got = a.align(pairs, algo=algo, **kw)
+        for (p, t), g in zip(pairs, got):
+            assert g == oracle.align(p, t, algo=algo, **kw), (algo, len(p))
+    a.close()
+
+
 def test_edge_cases_match_oracle(gpu, oracle):
     """empty batch, single characters, identical / unrelated sequences, all-N, very unequal lengths, lowercase"""
     assert gpu.align([]) == []

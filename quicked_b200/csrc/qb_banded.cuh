@@ -490,8 +490,9 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
 // serially exactly like the reference's inner loop (bpm_banded.c:238-261) — no cross-lane traffic at all.
 // The 32 leaves of a warp are interleaved in the matrix: entry (column c, band word w, lane l) lives at
 // group_base + (c*Bg + w)*32 + l, so every (Pv,Mv) store of the warp is one coalesced 512-byte line group.
-// The lane's 5 match masks per live block are staged in shared memory ([slot][thread], conflict-free) once per
-// 64 columns; the per-column fetch is an LDS indexed by the column's code.
+// The lane's 5 match masks per live block sit in shared memory ([slot][thread], conflict-free); at every 64-column
+// band shift they move up one slot and only the block that enters the band is fetched (3 x 16 B from the
+// [block][6] table); the per-column fetch is an LDS indexed by the column's code.
 template <int BMAX>
 __global__ void __launch_bounds__(128, 5)
 k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,

@@ -4,9 +4,10 @@
 // score only (reference quicked.c:178-199 -> bpm_windowed.c:563-628 with W=2, O=1, SCORE_ONLY).
 //
 // Mapping: ONE PAIR PER THREAD, persistent grid.  A 2-word window offers only a 2-way wavefront, so throughput comes
-// from pairs in flight.  Only what the walk can read is kept: the bottom-right 64x64 quadrant of the window (65
-// columns of one funnel-shifted 64-row slice of Pv and Mv — the reference keeps all 130 columns x 2 words,
-// bpm_windowed.c:143).  The 10 window-aligned match masks live in shared memory ([slot][thread], conflict-free).
+// from pairs in flight.  Only what the walk can read is kept: the bottom-right 64x64 quadrant of the window (the
+// reference keeps all 130 columns x 2 words, bpm_windowed.c:143) — for full windows as 64 u32 of walk decisions in
+// shared memory (SLIM, below), otherwise as 65 columns of one funnel-shifted 64-row slice of Pv and Mv in an L2/HBM
+// scratch.  The 10 window-aligned match masks live in shared memory ([slot][thread], conflict-free).
 //
 // SSE=true reproduces the observable behaviour of windowed_compute_window_sse (bpm_windowed.c:283-445), which is
 // what the reference runs on x86 unless force_scalar is set (dispatch :577); SSE=false follows the scalar
@@ -18,8 +19,8 @@
 namespace qb {
 
 constexpr int kWsThreads = 128;                 // threads per CTA of the WindowEd(S) kernel
-constexpr int kWsCtasPerSm = 6;                 // up to 768 resident threads per SM (register budget 85 per thread)
-constexpr int kWsResidentCtas = 4;              // CTAs per SM actually launched (scratch = 16.6 KB per resident CTA-thread group)
+constexpr int kWsCtasPerSm = 6;                 // launch bound: register budget 85 per thread
+constexpr int kWsResidentCtas = 4;              // CTAs per SM actually launched (SLIM: 43.5 KB of shared memory each; measured best)
 constexpr int kWsQuadSlots = 65 * 2;            // u64 slots per thread in the quadrant scratch ([slot][thread] layout)
 
 // SLIM: instead of the 64-row words of Pv and Mv, column s (1..64) of the quadrant keeps the walk's DECISION for the
@@ -274,8 +275,7 @@ k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigne
     const int T = kWsThreads, t = threadIdx.x;
     u64 *weq = s_weq + t;
     const i64 gtid = (i64)blockIdx.x * T + t, nthr = (i64)gridDim.x * T;
-    // Quadrant scratch: [slot][resident thread] in HBM/L2 (reused window after window, pair after pair, so it stays
-    // L2-resident); a shared-memory copy would cap the SM at ~200 threads and leave it latency-bound.
+    // Quadrant scratch of non-full and redone windows: [slot][resident thread] in HBM/L2 (reused window after window).
     u64 *qpv = quad + gtid;                                  // slot s at qpv[s * nthr]
     u64 *qmv = quad + 65 * nthr + gtid;
     const int hew_lim = 64 * hew_threshold / 100;            // (W-O)*64*thr/100, bpm_windowed.c:555

@@ -331,6 +331,20 @@ def main():
                 "ops_per_word_step": 24, "word_steps_per_step": st["word_steps"],
                 "peak_source": "qb200_measure_int_peak (LOP3+IADD3 microbenchmark, this run)"}
 
+    # the other two big kernels, for the record (not the `roofline` contract object): WindowEd(S) against the measured
+    # integer peak, the traceback against HBM (16-byte entry per visited text column; it is latency-, not bandwidth-bound)
+    others = []
+    if stage_avg.get("ms_windowed_s", 0) > 0 and int_peak:
+        a = 24.0 * st["word_steps_windowed"] / (stage_avg["ms_windowed_s"] * 1e-3) / 1e12
+        others.append({"kernel": "k_windowed21_score (WindowEd(S) bound)", "bound": "int_alu", "achieved": a, "peak": int_peak,
+                       "unit": "T int32-op/s", "frac": a / int_peak, "ms_per_launch": stage_avg["ms_windowed_s"]})
+    if stage_avg.get("ms_align_trace", 0) > 0 and args.workload in ("c1", "c2"):
+        tb = 16.0 * n_pairs * length
+        a = tb / (stage_avg["ms_align_trace"] * 1e-3) / 1e9
+        others.append({"kernel": "k_traceback_thread (BandEd traceback)", "bound": "hbm_latency", "achieved": a, "peak": peaks.get("hbm_gbs"),
+                       "unit": "GB/s", "frac": a / peaks.get("hbm_gbs"), "algorithmic_bytes": tb, "ms_per_launch": stage_avg["ms_align_trace"],
+                       "traffic": ncu_traffic_bytes("k_traceback_thread") if (args.workload == "c2" and n_pairs == 1000000 and args.algo == "quicked") else None})
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "c5":
         per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000, "c5": 50}[args.workload]
@@ -347,7 +361,7 @@ def main():
                "gcups_equiv": value * length * length / 1e9,
                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(st_e["h2d_bytes"]),
                        "d2h_bytes_per_step": int(st_e["d2h_bytes"])},
-               "gpu_launches": int(launches), "roofline": roof, "int_alu_roofline": int_roof, "cpu_baseline": cpu,
+               "gpu_launches": int(launches), "roofline": roof, "int_alu_roofline": int_roof, "other_kernel_rooflines": others, "cpu_baseline": cpu,
                "clocks": clocks, "stage_ms_per_step": stage_avg, "dominant_stage": dom,
                "pairs_ok_fraction": ok_frac, "mean_score": float(score.mean())}
         print(json.dumps(out))

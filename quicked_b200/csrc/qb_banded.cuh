@@ -351,11 +351,18 @@ k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ li
 // Full-matrix BandEd of ONE leaf by one thread (see k_banded_thread).  mat: first entry of this leaf, column stride
 // cs / word stride wsd (entries); ranges: live range per 64-column block, stride rstride; s_eq: this thread's
 // BMAX*5 shared-memory slots, stride T.
+constexpr int kThreadLeafWordStride = 32;   // entries between consecutive band words of a thread-kernel leaf (= lanes per group)
+constexpr int kThreadFillThreads = 128;     // threads per CTA of every kernel that calls banded_thread_fill
 template <int BMAX>
 __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int rev, const u64 *__restrict__ pq, int nbp,
-                                                   const unsigned char *__restrict__ tcodes, ulonglong2 *mat, i64 cs, i64 wsd,
-                                                   int2 *ranges, i64 rstride, u64 *s_eq, int T, u64 &ws)
+                                                   const unsigned char *__restrict__ tcodes, ulonglong2 *mat, i64 cs, i64 wsd_,
+                                                   int2 *ranges, i64 rstride, u64 *s_eq, int T_, u64 &ws)
 {
+        // Both strides are fixed by the callers (32 interleaved leaves per group, 128 threads per CTA); as compile-time
+        // constants they fold into the LDS / STG immediates instead of costing ~7 integer instructions per word-step.
+        constexpr i64 wsd = kThreadLeafWordStride;
+        constexpr int T = kThreadFillThreads;
+        (void)wsd_; (void)T_;
         const BandGeom g = band_geometry(m, n, cutoff);
         const int B = (int)g.Bc, prolog = (int)g.prolog;
         const int nblk = (m + 63) >> 6, mmod = m & 63, clamp = nblk - 1;

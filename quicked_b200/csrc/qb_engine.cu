@@ -297,7 +297,7 @@ int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks
 {
     if (n_tasks <= 0) return 0;
     if (!peq_base) peq_base = ctx->d_peq.as<u64>();
-    const int T = 128;
+    const int T = kThreadFillThreads;
     const size_t smem = (size_t)kThreadBandMax * kAlpha * T * 8;
     auto kern = k_banded_thread<kThreadBandMax>;
     if (const char *e = getenv("QB200_FILL_CARVE")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));

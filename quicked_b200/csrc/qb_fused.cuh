@@ -38,6 +38,7 @@ k_quicked_fused(const PairRec *__restrict__ pairs, int n_pairs, const unsigned c
 {
     __shared__ u64 s_mem[kFusedBandMax * kAlpha * kWsThreads];      // WindowEd uses the first 10 slots per thread, the fill all 20
     constexpr int T = kWsThreads;
+    static_assert(kWsThreads == kThreadFillThreads, "banded_thread_fill is compiled for this CTA size");
     const int t = threadIdx.x, lane = t & 31;
     u64 *s_thr = s_mem + t;
     const i64 gtid = (i64)blockIdx.x * T + t, nthr = (i64)gridDim.x * T;

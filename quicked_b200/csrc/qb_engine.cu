@@ -1431,6 +1431,8 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     i64 sub = (i64)sms * kWsResidentCtas * kWsThreads * 2;
+    // long reads: keep a sub-batch under ~768 MB of characters (its codes, match masks and traceback pool scale with it)
+    if (n > 0 && b->seqs_bytes / n > 0) sub = std::min(sub, std::max<i64>(1024, ((i64)768 << 20) / (b->seqs_bytes / n)));
     if (const char *e = getenv("QB200_SUB_PAIRS")) sub = std::max<i64>(1024, atoll(e));
     // Sub-batch boundaries: full-size sub-batches in the middle, a ramp of smaller ones at both ends so that the
     // first upload (nothing to overlap with) and the last compute + download (nothing left to overlap) are short.

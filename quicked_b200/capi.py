@@ -270,6 +270,28 @@ class BatchAligner:
         self._lib.qb200_get_stats(self._h, C.byref(s))
         return s.as_dict()
 
+    def align_batch(self, pairs, params=None, **kw):
+        """qb200_align_batch (host in / host out; pipelined for big jobs) -> list of (status, score, cigar-or-None)"""
+        seqs, po, pl, to, tl = pack_pairs(pairs)
+        n = int(po.size)
+        p = params if params is not None else make_params(**kw)
+        score = np.empty(n, np.int32); status = np.empty(n, np.int32); off = np.zeros(n + 1, np.int64)
+        cig = np.zeros(int(seqs.size) // 2 + 1024, np.uint8)
+        b = self._batch(seqs.ctypes.data, int(seqs.size), n, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data)
+        r = Results(score.ctypes.data, status.ctypes.data, cig.ctypes.data, int(cig.size), off.ctypes.data, 0)
+        rc = self._lib.qb200_align_batch(self._h, C.byref(p), C.byref(b), C.byref(r))
+        if rc == QB200_ERR_CAPACITY:
+            cig = np.zeros(int(r.cigar_bytes) + 16, np.uint8)
+            r = Results(score.ctypes.data, status.ctypes.data, cig.ctypes.data, int(cig.size), off.ctypes.data, 0)
+            rc = self._lib.qb200_align_batch(self._h, C.byref(p), C.byref(b), C.byref(r))
+        self._check(rc, "qb200_align_batch")
+        raw = cig.tobytes()
+        out = []
+        for i in range(n):
+            c = raw[off[i]:off[i + 1] - 1].decode() if off[i + 1] - off[i] > 1 else None
+            out.append((int(status[i]), int(score[i]), c))
+        return out
+
     def align(self, pairs, params=None, **kw):
         """-> list of (status, score, cigar-or-None), one tuple per pair"""
         self.upload_arrays(*pack_pairs(pairs))

@@ -1585,7 +1585,11 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
 int qb200_align_batch(qb200_ctx_t *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res)
 {
     if (!ctx || !params || !b || !res) return QB200_ERR_ARG;
-    if (b->n_pairs >= 200000 && !getenv("QB200_NO_PIPELINE")) return align_batch_pipelined(ctx, params, b, res);
+    // big jobs (many pairs, or many characters: 100 k pairs of 10 kbp are 2 GB) overlap H2D, kernels and D2H
+    i64 min_pairs = 200000;
+    if (const char *e = getenv("QB200_PIPELINE_MIN_PAIRS")) min_pairs = std::max<i64>(2, atoll(e));
+    const bool big = b->n_pairs >= min_pairs || (b->n_pairs >= 4096 && b->seqs_bytes >= ((i64)512 << 20));
+    if (big && !getenv("QB200_NO_PIPELINE")) return align_batch_pipelined(ctx, params, b, res);
     int rc = qb200_upload(ctx, b);
     if (rc) return rc;
     rc = qb200_run(ctx, params);

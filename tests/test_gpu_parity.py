@@ -384,6 +384,25 @@ def test_small_matrix_pool_chunks_the_batch(oracle, monkeypatch):
     a.close()
 
 
+def test_pipelined_path_with_long_reads_and_slow_pairs(oracle, monkeypatch):
+    """the pipelined qb200_align_batch on a batch that also holds warp-kernel leaves, Hirschberg splits and pairs that
+    go through WindowEd(L) / band doubling (forced on a small batch: 700 pairs per sub-batch)"""
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_PIPELINE_MIN_PAIRS", "1000")
+    monkeypatch.setenv("QB200_SUB_PAIRS", "1024")
+    pairs = generate_pairs(3000, 400, 0.1, seed=91) + generate_pairs(40, 6000, 0.2, seed=92) + \
+        generate_pairs(30, 3000, 0.05, seed=93, indels=(4, 200)) + generate_pairs(3, 40000, 0.15, seed=94) + [(b"", b"ACGT")]
+    rng = np.random.default_rng(3)
+    order = rng.permutation(len(pairs))
+    pairs = [pairs[i] for i in order]
+    a = qb.BatchAligner(device=0)
+    for algo, kw in ((0, {}), (3, dict(bandwidth=20))):
+        got = a.align_batch(pairs, algo=algo, **kw)
+        for (p, t), g in zip(pairs, got):
+            assert g == oracle.align(p, t, algo=algo, **kw), (algo, len(p))
+    a.close()
+
+
 def test_edge_cases_match_oracle(gpu, oracle):
     """empty batch, single characters, identical / unrelated sequences, all-N, very unequal lengths, lowercase"""
     assert gpu.align([]) == []

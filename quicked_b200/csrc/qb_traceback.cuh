@@ -329,6 +329,9 @@ struct TextSink {
     __device__ __forceinline__ void put_run(int len, int op)
     {
         unsigned x = (unsigned)len;
+        const u64 opc = (u64)(unsigned char)"MXID"[op];
+        if (x < 10u) { put((u64)('0' + x) | (opc << 8), 2); return; }                 // most runs are this short
+        if (x < 100u) { put((u64)('0' + x / 10u) | ((u64)('0' + x % 10u) << 8) | (opc << 16), 3); return; }
         const int nd = dec_digits(x);
         if (nd <= 7) {
             u64 chunk = (u64)(unsigned char)"MXID"[op] << (8 * nd);

@@ -54,7 +54,7 @@ def generate_c5(base_pairs, seed):
 ALGOS = {"quicked": 0, "windowed": 1, "banded": 2, "hirschberg": 3}
 
 
-def ncu_traffic_bytes(kernel_substr, csv_name="r1_ncu_full_c2_v6_raw.csv"):
+def ncu_traffic_bytes(kernel_substr, csv_name="r1_ncu_full_c2_v7_raw.csv"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel_substr`, from the committed `ncu --set full`
     capture of this same command (profiles/, 1 M pairs of configs[1]); None when the capture is not there."""
     import csv
@@ -297,7 +297,8 @@ def main():
         if rc != 0:
             raise RuntimeError(f"qb200_align_batch rc={rc}: {lib.qb200_last_error(gpu._h).decode()}")
 
-    e2e_step()
+    for _ in range(max(1, args.warmup)):          # the first calls create the pipeline's worker contexts and size their pools
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

@@ -254,7 +254,8 @@ def main():
     for _ in range(args.warmup):
         gpu.run(params)
     # one sampler per rank on its own GPU; QB_NO_SMI=1 disables it (nvidia-smi polling can perturb short steps)
-    sampler = ClockSampler(None if os.environ.get("QB_NO_SMI") else local_rank)
+    # one nvidia-smi poller is enough (rank 0 prints the line); eight of them only compete with the ranks for the driver
+    sampler = ClockSampler(None if (os.environ.get("QB_NO_SMI") or rank != 0) else local_rank)
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -120,6 +120,8 @@ struct qb200_ctx {
     DevBuf d_fmat, d_franges, d_done;      // fused fast path: per-resident-warp matrix slots, live ranges, per-pair done flags
     i64 ops_words_fused = 0;               // op words of all pairs (fused-path region of the op pool)
     int max_n = 0, max_m = 0;
+    int ws_carve_set[2][2] = {{-1, -1}, {-1, -1}};   // shared-memory carve-out already requested for each WindowEd(S) kernel variant
+    int sms = 0;                           // SM count of the device (queried once)
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
     static constexpr int kWorkers = 8;
@@ -572,8 +574,8 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     if (const char *e = getenv("QB200_FUSED")) use_fused = (prm.algo == QUICKED) && atoi(e) != 0;
     i64 leaf_base = 0, ops_base = 0;
     if (use_fused) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+        const int sms = ctx->sms;
         int fctas = kFusedCtasPerSm;
         if (const char *e = getenv("QB200_FUSED_CTAS")) fctas = std::max(1, std::min(atoi(e), (int)kFusedCtasPerSm));
         const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * fctas);   // persistent: one wave
@@ -613,8 +615,8 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     // ---- QUICKED stage 1: WindowEd(S) bound (quicked.c:178-199) ----
     if (prm.algo == QUICKED && !use_fused) {
         Span sp(ctx, ST_WS);
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+        const int sms = ctx->sms;
         int ctas = kWsResidentCtas;
         if (const char *e = getenv("QB200_WS_CTAS")) ctas = std::max(1, std::min(atoi(e), (int)kWsCtasPerSm));
         const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * ctas);   // persistent: one wave
@@ -628,7 +630,10 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         {   // carve out what the resident CTAs need (+1 KB per CTA of system use), the rest stays L1
             int carve = std::min(100, (ctas * (slim ? 45 : 11) * 100 + 227) / 228 + 1);
             if (const char *e = getenv("QB200_WS_CARVE")) carve = atoi(e);
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            if (ctx->ws_carve_set[prm.force_scalar ? 1 : 0][slim ? 1 : 0] != carve) {      // once per kernel variant, not per run
+                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+                ctx->ws_carve_set[prm.force_scalar ? 1 : 0][slim ? 1 : 0] = carve;
+            }
         }
         kern<<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
             ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(),
@@ -721,10 +726,11 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     rt.pt("plan synced");
     // ---- fast path: fill + traceback, chunked only if the traceback state exceeds the pool ----
     if (tot.leaf > 0) {
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, (size_t)((free_b + ctx->d_matrix.cap) * 0.85)) / 16);
         const i64 need = tot.matw + plan.mat_t;
+        // cudaMemGetInfo is a slow, cross-process serialising driver call: only ask when the pool has to grow
+        size_t free_b = 0, total_b = 0;
+        if ((size_t)need * 16 > ctx->d_matrix.cap) CK(cudaMemGetInfo(&free_b, &total_b));
+        const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, std::max(ctx->d_matrix.cap, (size_t)((free_b + ctx->d_matrix.cap) * 0.85))) / 16);
         if (need <= limit) {
             CK(ctx->d_matrix.reserve((size_t)need * 16));
             {

@@ -72,6 +72,27 @@ def ncu_traffic_bytes(kernel_substr, csv_name="r1_ncu_full_c2_v7_raw.csv"):
     return None
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One process per GPU on a multi-socket host: run this rank's threads (and so first-touch its pinned buffers) on the
+    CPUs of the GPU's NUMA node, /sys/bus/pci/devices/<bdf>/local_cpulist.  The end-to-end arm streams 2 GB per step per
+    GPU from host memory; across the socket interconnect the 8-GPU aggregate saturates early.  Returns the cpulist used."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -205,6 +226,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the QuickEd GPU path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = None
+    if world > 1 and not os.environ.get("QB_NO_AFFINITY"):
+        numa = bind_to_gpu_numa_node(torch, local_rank)       # before any pinned allocation: first touch stays node-local
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -363,7 +387,7 @@ def main():
                "gcups_equiv": value * length * length / 1e9,
                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(st_e["h2d_bytes"]),
                        "d2h_bytes_per_step": int(st_e["d2h_bytes"])},
-               "gpu_launches": int(launches), "roofline": roof, "int_alu_roofline": int_roof, "other_kernel_rooflines": others, "cpu_baseline": cpu,
+               "gpu_launches": int(launches), "host_affinity": numa, "roofline": roof, "int_alu_roofline": int_roof, "other_kernel_rooflines": others, "cpu_baseline": cpu,
                "clocks": clocks, "stage_ms_per_step": stage_avg, "dominant_stage": dom,
                "pairs_ok_fraction": ok_frac, "mean_score": float(score.mean())}
         print(json.dumps(out))

@@ -91,7 +91,12 @@ int qb200_get_stats(qb200_ctx_t *ctx, qb200_stats_t *stats);
  * (reference bpm_windowed.c:555-557).  Either pointer may be NULL.  n must equal the batch's n_pairs. */
 int qb200_get_bounds(qb200_ctx_t *ctx, int32_t *bound, int32_t *high_error_windows, int64_t n);
 
-/* --- one call, host in / host out: what a reference caller's batch loop is replaced by --- */
+/* --- one call, host in / host out: what a reference caller's batch loop is replaced by ---
+ * Big jobs (>= 200 000 pairs or >= 512 MB of characters) are cut into sub-batches and pipelined (H2D / kernels / D2H
+ * overlap); CIGAR strings still come back packed in input order.  Page-locked caller buffers (qb200_host_alloc or
+ * cudaHostRegister) avoid one staging copy.  On QB200_ERR_CAPACITY scores, statuses and cigar_bytes (the size needed)
+ * are valid: grow the cigar buffer and call again (a pipelined job keeps nothing on the device; after a small,
+ * unpipelined job qb200_download works too). */
 int qb200_align_batch(qb200_ctx_t *ctx, const quicked_params_t *params,
                       const qb200_batch_t *host_batch, qb200_results_t *host_results);
 

@@ -68,7 +68,7 @@ typedef struct {                  /* counters of the last qb200_run(); all times
             ms_cigar;
     int64_t matrix_bytes;         /* traceback state written to HBM (Pv/Mv columns)                        */
     float   ms_fused;             /* the fused WindowEd+BandEd+traceback kernel of the QUICKED fast path   */
-    int32_t pad_;
+    int32_t leaves_punted;        /* leaves the tile path handed to the exact full-matrix kernels (too-narrow bands)   */
     int64_t pairs_fused;          /* pairs completed by that kernel                                        */
 } qb200_stats_t;
 

@@ -224,6 +224,9 @@ int64_t qo_banded_score(const char *pattern, int m, const char *text, int n, int
 typedef struct { char *ops; int64_t begin, end; } ops_t;
 static inline void ops_push_front(ops_t *o, char c) { o->ops[--o->begin] = c; }
 
+static __thread uint64_t *g_dump_pv, *g_dump_mv;   /* test hooks, see qo_banded_full_dump */
+static __thread int64_t *g_dump_ranges;
+
 /* BandEd full matrix + traceback (a leaf): bpm_banded.c:199-316 fill, :967-1036 walk.
  * The walk's ops are pushed in front of whatever `out` already holds (cigar.c:179-188). */
 static int64_t banded_full(const pat_t *p, const char *text, int64_t n, int64_t cutoff, ops_t *out)
@@ -239,11 +242,19 @@ static int64_t banded_full(const pat_t *p, const char *text, int64_t n, int64_t 
     memset(MV, 0, (size_t)B * (size_t)(n + 1) * 8);
     b.scores = (int64_t *)calloc((size_t)(p->nblk + B + 2), 8);
     band_reset(&b, B, PV, MV);
+    if (g_dump_ranges) { g_dump_ranges[0] = b.first; g_dump_ranges[1] = b.last; }
     for (int64_t col = 0; col < n; ++col) {
         band_column(&b, p, enc(text[col]), PV + col * B, MV + col * B, PV + (col + 1) * B, MV + (col + 1) * B);
-        if ((col + 1) % W64 == 0) band_shift(&b, PV + (col + 1) * B, MV + (col + 1) * B, p->nblk - 1);
+        if ((col + 1) % W64 == 0) {
+            band_shift(&b, PV + (col + 1) * B, MV + (col + 1) * B, p->nblk - 1);
+            if (g_dump_ranges) { g_dump_ranges[2 * b.pos_h] = b.first; g_dump_ranges[2 * b.pos_h + 1] = b.last; }
+        }
     }
     const int64_t band_score = band_final_score(&b, p);
+    if (g_dump_pv) {   /* test hook (qo_banded_full_dump): the stored matrix exactly as the walk below reads it */
+        memcpy(g_dump_pv, PV, (size_t)B * (size_t)(n + 1) * 8);
+        memcpy(g_dump_mv, MV, (size_t)B * (size_t)(n + 1) * 8);
+    }
     /* walk: D if Pv[col h+1] bit v; else I if Mv[col h] bit v; else M/X on RAW bytes (:1002-1023) */
     int64_t h = n - 1, v = p->m - 1;
     while (v >= 0 && h >= 0) {
@@ -263,6 +274,22 @@ static int64_t banded_full(const pat_t *p, const char *text, int64_t n, int64_t 
     while (v >= 0) { ops_push_front(out, 'D'); --v; }
     free(PV); free(MV); free(b.scores);
     return band_score;
+}
+
+/* Test hook: one BandEd leaf (full matrix + walk) with its stored matrix and live ranges exported.
+ * pv/mv: B_cigar*(n+1) words each ([column][band word], never-written words 0); ranges: (first,last) per 64-column
+ * block, n/64+1 pairs; ops: the walk's op string (m+n+1 bytes).  Returns the band score. */
+int64_t qo_banded_full_dump(const char *pattern, int m, const char *text, int n, int64_t cutoff, uint64_t *pv,
+                            uint64_t *mv, int64_t *ranges, char *ops)
+{
+    pat_t p; pat_build(&p, pattern, m);
+    ops_t o; o.ops = (char *)malloc((size_t)m + (size_t)n + 1); o.begin = o.end = (int64_t)m + n;
+    g_dump_pv = pv; g_dump_mv = mv; g_dump_ranges = ranges;
+    const int64_t s = banded_full(&p, text, n, cutoff, &o);
+    g_dump_pv = g_dump_mv = NULL; g_dump_ranges = NULL;
+    if (ops) { memcpy(ops, o.ops + o.begin, (size_t)(o.end - o.begin)); ops[o.end - o.begin] = 0; }
+    free(o.ops); pat_free(&p);
+    return s;
 }
 
 /* ------------------------------------------------------------------------------------------------

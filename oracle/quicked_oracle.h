@@ -77,6 +77,12 @@ qo_band_geom_t qo_band_geometry(int64_t m, int64_t n, int64_t cutoff);
 int64_t qo_banded_score(const char *pattern, int m, const char *text, int n, int64_t cutoff, int64_t finish,
                         uint64_t *pv, uint64_t *mv, int64_t *scores, int64_t *lower_block, int64_t *higher_block);
 
+/* Test hook: one BandEd leaf (bpm_banded.c:199-316 fill + :967-1036 walk) with the stored matrix exported.
+ * pv/mv: B_cigar*(n+1) words each, [column][band word]; ranges: (first,last) per 64-column block (n/64+1 pairs);
+ * ops: the walk's op string, m+n+1 bytes.  Any pointer may be NULL except pattern/text. */
+int64_t qo_banded_full_dump(const char *pattern, int m, const char *text, int n, int64_t cutoff, uint64_t *pv,
+                            uint64_t *mv, int64_t *ranges, char *ops);
+
 /* WindowEd score-only (bpm_windowed.c:563-628 with SCORE_ONLY). sse!=0 emulates windowed_compute_window_sse
  * (only meaningful for W==2). Returns the score estimate, *hew = high-error-window count. */
 int64_t qo_windowed_score(const char *pattern, int m, const char *text, int n, int W, int O,

@@ -57,7 +57,7 @@ class Stats(C.Structure):         # qb200_stats_t
                                          "pairs_stage3", "banded_tries", "hirschberg_splits", "leaves")] + \
                [(k, C.c_float) for k in ("ms_total", "ms_prepare", "ms_windowed_s", "ms_windowed_l", "ms_banded",
                                          "ms_align_fill", "ms_align_trace", "ms_cigar")] + [("matrix_bytes", C.c_int64)] + \
-               [("ms_fused", C.c_float), ("pad_", C.c_int32), ("pairs_fused", C.c_int64)]
+               [("ms_fused", C.c_float), ("leaves_punted", C.c_int32), ("pairs_fused", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

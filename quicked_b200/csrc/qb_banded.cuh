@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128)
 k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
               const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
               int *__restrict__ scores_pool, u64 *__restrict__ state_pool, int2 *__restrict__ range_pool,
-              BandOut *__restrict__ outs, u64 *__restrict__ counters)
+              BandOut *__restrict__ outs, u64 *__restrict__ counters, int min_B)
 {
     constexpr int kCap = BandedSmem<R>::kCap;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,7 +55,7 @@ k_banded_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, 
     const int B = (int)(FULL ? g.Bc : g.Bs);
     {   // tasks of other band heights are handled by the launch of their own R (one list, one launch per R)
         const int need = B <= 32 ? 1 : B <= 64 ? 2 : B <= 128 ? 4 : B <= 256 ? 8 : B <= 512 ? 16 : B <= 1024 ? 32 : 64;
-        if (need != R) return;
+        if (need != R || B < min_B) return;                          // min_B: narrower bands belong to the tile kernels
     }
     const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63;
     const int clamp = FULL ? nblk - 1 : nblk;                       // bpm_banded.c:295 vs :917
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(32)
 k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
                   const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
                   int *__restrict__ scores_pool, u64 *__restrict__ state_pool, int2 *__restrict__ range_pool,
-                  BandOut *__restrict__ outs, u64 *__restrict__ counters, int cap)
+                  BandOut *__restrict__ outs, u64 *__restrict__ counters, int cap, int min_B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
@@ -238,7 +238,7 @@ k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ li
     tk.mat_off -= mat_sub;
     const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
     const int B = (int)(FULL ? g.Bc : g.Bs);
-    if (B <= 1024) return;                                           // handled by the R-templated launches
+    if (B <= 1024 || B < min_B) return;                              // handled by the R-templated launches / the tile kernels
     u64 *s_pv = reinterpret_cast<u64 *>(smem_raw);
     u64 *s_mv = s_pv + cap;
     const int nblk = (tk.m + 63) >> 6, mmod = tk.m & 63;

@@ -120,7 +120,7 @@ __device__ __forceinline__ unsigned enc_stored(unsigned c)
 }
 
 // One Myers block update with bit-63 carry-out (reference bpm_commons.h:82-101).
-__device__ __forceinline__ void myers_step(u64 eq, u64 &pv, u64 &mv, u32 hp_in, u32 hm_in, u32 &hp_out, u32 &hm_out)
+__host__ __device__ __forceinline__ void myers_step(u64 eq, u64 &pv, u64 &mv, u32 hp_in, u32 hm_in, u32 &hp_out, u32 &hm_out)
 {
     const u64 xv = eq | mv;
     const u64 eqh = eq | (u64)hm_in;
@@ -154,7 +154,7 @@ __device__ __forceinline__ void myers_step_hv(u64 eq, u64 &pv, u64 &mv, u32 hp_i
 }
 
 // Same update, carry-out taken at bit `ob` (reference bpm_commons.h:49-68 with level_mask = 1<<ob).
-__device__ __forceinline__ void myers_step_at(u64 eq, u64 &pv, u64 &mv, u32 hp_in, u32 hm_in, int ob,
+__host__ __device__ __forceinline__ void myers_step_at(u64 eq, u64 &pv, u64 &mv, u32 hp_in, u32 hm_in, int ob,
                                               u32 &hp_out, u32 &hm_out)
 {
     const u64 xv = eq | mv;
@@ -193,7 +193,7 @@ __device__ __forceinline__ u64 funnel_r(u64 lo, u64 hi, unsigned sh)   // (hi:lo
     return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
 }
 
-__device__ __forceinline__ int dec_digits(unsigned v)
+__host__ __device__ __forceinline__ int dec_digits(unsigned v)
 {
     if (v < 100u) return v < 10u ? 1 : 2;               // the common case: short runs
     return v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7

@@ -26,6 +26,8 @@
 #include "qb_plan.cuh"
 #include "qb_prep.cuh"
 #include "qb_traceback.cuh"
+#include "qb_tiles.cuh"
+#include "qb_tiletrace.cuh"
 #include "qb_windowed.cuh"
 
 using namespace qb;
@@ -122,6 +124,8 @@ struct qb200_ctx {
     int max_n = 0, max_m = 0;
     int ws_carve_set[2][2] = {{-1, -1}, {-1, -1}};   // shared-memory carve-out already requested for each WindowEd(S) kernel variant
     int sms = 0;                           // SM count of the device (queried once)
+    DevBuf d_tclass, d_tctl, d_punt, d_gather;   // tile path: per-class task lists, counters, punted tasks
+    bool use_tiles = true;
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
     static constexpr int kWorkers = 8;
@@ -235,7 +239,7 @@ int finish_upload(qb200_ctx *ctx)
 }
 
 template <int R, bool FULL>
-int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base)
+int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base, int min_B)
 {
     if (n_tasks <= 0) return 0;
     const int bpw = BandedSmem<R>::kBytesPerWarp;
@@ -247,7 +251,7 @@ int launch_banded_r(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, 
     kern<<<blocks, wpb * 32, smem, ctx->stream>>>(d_tasks, d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(),
                                                    peq_base, ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(),
                                                    ctx->d_state.as<u64>(), ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(),
-                                                   ctx->d_counters.as<u64>());
+                                                   ctx->d_counters.as<u64>(), min_B);
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
     return 0;
@@ -261,7 +265,7 @@ int rounds_for(i64 B)                  // 64 = the dynamic (shared-memory reside
 }
 
 template <bool FULL>
-int launch_banded_dyn(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base)
+int launch_banded_dyn(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base, int min_B)
 {
     if (n_tasks <= 0) return 0;
     const int cap = (int)kDynBandMax + 2;
@@ -270,7 +274,7 @@ int launch_banded_dyn(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_tasks, 32, smem, ctx->stream>>>(d_tasks, d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(), peq_base,
                                              ctx->d_matrix.as<ulonglong2>(), ctx->d_scores.as<int>(), ctx->d_state.as<u64>(),
-                                             ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(), ctx->d_counters.as<u64>(), cap);
+                                             ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(), ctx->d_counters.as<u64>(), cap, min_B);
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
     return 0;
@@ -279,19 +283,20 @@ int launch_banded_dyn(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list
 // One launch per band-height class present in the list (each warp exits at once if its task belongs to another class).
 template <bool FULL>
 int launch_banded(qb200_ctx *ctx, unsigned r_mask, const BandTask *d_tasks, const int *d_list, int begin, int n_tasks, i64 mat_sub,
-                  const u64 *peq_base = nullptr)
+                  const u64 *peq_base = nullptr, int min_B = 0)
 {
     if (!peq_base) peq_base = ctx->d_peq.as<u64>();
     int rc = 0;
-    if (!rc && (r_mask & 1)) rc = launch_banded_r<1, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
-    if (!rc && (r_mask & 2)) rc = launch_banded_r<2, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
-    if (!rc && (r_mask & 4)) rc = launch_banded_r<4, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
-    if (!rc && (r_mask & 8)) rc = launch_banded_r<8, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
-    if (!rc && (r_mask & 16)) rc = launch_banded_r<16, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
-    if (!rc && (r_mask & 32)) rc = launch_banded_r<32, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
-    if (!rc && (r_mask & 64)) rc = launch_banded_dyn<FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base);
+    if (!rc && (r_mask & 1)) rc = launch_banded_r<1, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base, min_B);
+    if (!rc && (r_mask & 2)) rc = launch_banded_r<2, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base, min_B);
+    if (!rc && (r_mask & 4)) rc = launch_banded_r<4, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base, min_B);
+    if (!rc && (r_mask & 8)) rc = launch_banded_r<8, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base, min_B);
+    if (!rc && (r_mask & 16)) rc = launch_banded_r<16, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base, min_B);
+    if (!rc && (r_mask & 32)) rc = launch_banded_r<32, FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base, min_B);
+    if (!rc && (r_mask & 64)) rc = launch_banded_dyn<FULL>(ctx, d_tasks, d_list, begin, n_tasks, mat_sub, peq_base, min_B);
     return rc;
 }
+constexpr int kTileBandMax = kTileMaxRing - 2;      // widest band (blocks) the tile kernels take
 
 constexpr int kThreadBandMax = 4;
 
@@ -311,13 +316,13 @@ int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks
     return 0;
 }
 
-int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub, bool warp_layout = false)
+int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub, bool warp_layout = false, int min_B = 0)
 {
     if (n_tasks <= 0) return 0;
     if (warp_layout) {      // leaves written by the warp kernel: cooperative, tile-prefetching walk
         k_traceback_warp<<<(n_tasks + kTraceWarpsPerCta - 1) / kTraceWarpsPerCta, 32 * kTraceWarpsPerCta, 0, ctx->stream>>>(
             ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub, ctx->raw(), ctx->d_matrix.as<ulonglong2>(),
-            ctx->d_ranges.as<int2>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>());
+            ctx->d_ranges.as<int2>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>(), min_B);
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
         return 0;
@@ -332,8 +337,146 @@ int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, 
     return 0;
 }
 
+// ---- tile path (qb_tiles.cuh / qb_tiletrace.cuh) ----------------------------------------------------------------
+constexpr int kTileClasses = 8;                     // ring sizes 8 << c: bands up to kTileMaxRing - 2 blocks
+struct TileCtl { int counts[kTileClasses]; int next[kTileClasses]; int punt_count; int pad_[15]; };
+inline bool tile_band_ok(i64 B) { return tile_ring_for(B) <= kTileMaxRing; }
+
+template <bool FULL, int LANES>
+int launch_tiles_class(qb200_ctx *ctx, const TilePools &P, int c, int cap, int n_bound)
+{
+    const int RB = 8 << c;
+    const size_t fixed = tile_smem_bytes(RB, 0, LANES), per = tile_slot_arena_bytes(RB) + sizeof(TileSlot);
+    const size_t budget = (RB <= 128 ? 72 : 110) * 1024;
+    int nslots = (int)((budget > fixed ? budget - fixed : 0) / per);
+    nslots = std::max(1, std::min(32, nslots));
+    if (const char *e = getenv("QB200_TILE_SLOTS")) nslots = std::max(1, std::min(32, atoi(e)));
+    const size_t smem = tile_smem_bytes(RB, nslots, LANES);
+    auto kern = k_band_tiles<FULL, LANES>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+    int occ = (int)((227 * 1024) / (smem + 1024));
+    occ = std::max(1, std::min(occ, 2048 / (LANES + 32)));
+    const int blocks = std::max(1, std::min(ctx->sms * occ, (n_bound + nslots - 1) / nslots));
+    TileCtl *ctl = ctx->d_tctl.as<TileCtl>();
+    TileLaunch Q;
+    Q.list = ctx->d_tclass.as<int>() + (size_t)c * cap; Q.count = &ctl->counts[c]; Q.next = &ctl->next[c];
+    Q.counters = ctx->d_counters.as<u64>(); Q.RB = RB; Q.nslots = nslots; Q.lanes = LANES;
+    kern<<<blocks, LANES + 32, smem, ctx->stream>>>(P, Q);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return 0;
+}
+
+// BandEd fill of tasks[list[begin .. begin+n)] by the tile kernels, one launch per band-height class in class_mask.
+// FULL: writes tile records (pool d_matrix, task.mat_off in 16-byte units) + live ranges; !FULL: score-only passes.
+// Tasks the kernels give up on: FULL -> BandOut.pos_v = kTilePunted; !FULL -> appended to d_punt (count in d_tctl).
+template <bool FULL>
+int launch_tiles(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base,
+                 unsigned class_mask = 0xffu)
+{
+    if (n <= 0) return 0;
+    CK(ctx->d_tclass.reserve((size_t)kTileClasses * (size_t)n * 4));
+    CK(ctx->d_tctl.reserve(sizeof(TileCtl)));
+    CK(ctx->d_punt.reserve((size_t)n * 4 + 16));
+    CK(cudaMemsetAsync(ctx->d_tctl.p, 0, sizeof(TileCtl), ctx->stream));
+    k_tile_classes<FULL><<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_tclass.as<int>(), n, ctx->d_tctl.as<TileCtl>()->counts);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    TilePools P;
+    P.tasks = d_tasks; P.codes = ctx->d_codes.as<unsigned char>(); P.peq = peq_base; P.recs = ctx->d_matrix.as<TileRec>();
+    P.ranges = ctx->d_ranges.as<int2>(); P.scores = ctx->d_scores.as<int>(); P.state = ctx->d_state.as<u64>();
+    P.outs = ctx->d_bandout.as<BandOut>(); P.punt_list = ctx->d_punt.as<int>(); P.punt_count = &ctx->d_tctl.as<TileCtl>()->punt_count;
+    P.rec_sub = sub;
+    for (int c = 0; c < kTileClasses; ++c) {
+        if (!((class_mask >> c) & 1u)) continue;
+        int rc;
+        if (c == 0) rc = launch_tiles_class<FULL, 32>(ctx, P, c, n, n);
+        else if (c == 1) rc = launch_tiles_class<FULL, 64>(ctx, P, c, n, n);
+        else rc = launch_tiles_class<FULL, 128>(ctx, P, c, n, n);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+inline unsigned tile_class_bit(i64 B)
+{
+    const int rb = tile_ring_for(B);
+    int c = 0;
+    while ((8 << c) < rb) ++c;
+    return 1u << c;
+}
+
+int launch_tile_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base)
+{
+    if (n <= 0) return 0;
+    k_traceback_tiles<<<(n + kTileTraceThreads - 1) / kTileTraceThreads, kTileTraceThreads, 0, ctx->stream>>>(
+        ctx->d_leaves.as<BandTask>(), d_list, begin, n, sub, ctx->d_codes.as<unsigned char>(), ctx->raw(), peq_base, ctx->d_matrix.as<TileRec>(),
+        ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>(), ctx->d_punt.as<int>(),
+        &ctx->d_tctl.as<TileCtl>()->punt_count);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return 0;
+}
+
+__global__ void k_gather_tasks(const BandTask *tasks, const int *ids, int n, BandTask *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tasks[ids[i]];
+}
+__global__ void k_scatter_tasks(BandTask *tasks, const int *ids, int n, const BandTask *in)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tasks[ids[i]] = in[i];
+}
+
+// Leaves the tile path punted on (walk outside the live band, empty band): redo them with the exact full-matrix
+// kernels (warp fill in the reference's [column][word] layout + the thread walk, 2-bit ops).  Synchronises.
+int rerun_punted_leaves(qb200_ctx *ctx, const u64 *peq_base)
+{
+    int cnt = 0;
+    CK(cudaMemcpyAsync(ctx->h_pinned + 128, &ctx->d_tctl.as<TileCtl>()->punt_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cnt = *reinterpret_cast<int *>(ctx->h_pinned + 128);
+    ctx->stats.leaves_punted += cnt;
+    if (cnt <= 0) return 0;
+    std::vector<BandTask> tk((size_t)cnt);
+    CK(ctx->d_gather.reserve(sizeof(BandTask) * (size_t)cnt));
+    k_gather_tasks<<<(cnt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), ctx->d_punt.as<int>(), cnt, ctx->d_gather.as<BandTask>());
+    CK(cudaMemcpyAsync(tk.data(), ctx->d_gather.p, sizeof(BandTask) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, (size_t)((free_b + ctx->d_matrix.cap) * 0.85)) / 16);
+    for (int q0 = 0; q0 < cnt;) {
+        i64 ent = 0; int q1 = q0; unsigned mask = 0;
+        while (q1 < cnt) {
+            BandTask &t = tk[(size_t)q1];
+            const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
+            const i64 e = (i64)(t.n + 1) * g.Bc;
+            if (q1 > q0 && ent + e > limit) break;
+            const int R = rounds_for(g.Bc);
+            if (!R) { ctx->err = "leaf band of " + std::to_string(g.Bc) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
+            mask |= (unsigned)R;
+            t.mat_off = ent; t.mat_cs = (int)g.Bc; t.mat_ws = 1;
+            ent += e; ++q1;
+        }
+        if ((size_t)ent * 16 > free_b + ctx->d_matrix.cap) { ctx->err = "a single traceback matrix does not fit the device"; return QB200_ERR_OOM; }
+        CK(cudaMemcpyAsync(ctx->d_gather.as<BandTask>() + q0, tk.data() + q0, sizeof(BandTask) * (size_t)(q1 - q0), cudaMemcpyHostToDevice, ctx->stream));
+        k_scatter_tasks<<<(q1 - q0 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), ctx->d_punt.as<int>() + q0, q1 - q0, ctx->d_gather.as<BandTask>() + q0);
+        CK(ctx->d_matrix.reserve((size_t)ent * 16));
+        { Span sp(ctx, ST_FILL); int rc = launch_banded<true>(ctx, mask, ctx->d_leaves.as<BandTask>(), ctx->d_punt.as<int>(), q0, q1 - q0, 0, peq_base); if (rc) return rc; }
+        { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_punt.as<int>(), q0, q1 - q0, 0, false); if (rc) return rc; }
+        ctx->stats.matrix_bytes += ent * 16;
+        CK(cudaStreamSynchronize(ctx->stream));
+        q0 = q1;
+    }
+    return 0;
+}
+
 // Largest e in (s, n] such that the entries of items s..e-1 fit `limit` (at least one item).  One thread, binary search.
-__global__ void k_chunk_end_groups(const i64 *goff, const i64 *gsize, int n, int s, i64 limit, int *out)
+// out[0] = e, ent[0] = entries of the chunk (can exceed `limit` when a single item does: the caller grows the pool or fails)
+__global__ void k_chunk_end_groups(const i64 *goff, const i64 *gsize, int n, int s, i64 limit, int *out, i64 *ent)
 {
     int lo = s + 1, hi = n;
     while (lo < hi) {
@@ -341,23 +484,32 @@ __global__ void k_chunk_end_groups(const i64 *goff, const i64 *gsize, int n, int
         if (goff[mid - 1] + gsize[mid - 1] - goff[s] <= limit) lo = mid; else hi = mid - 1;
     }
     out[0] = lo;
+    ent[0] = goff[lo - 1] + gsize[lo - 1] - goff[s];
 }
-__global__ void k_chunk_end_leaves(const BandTask *leaves, const int *list, int n, int s, i64 limit, int *out, i64 *start_off)
+__device__ __forceinline__ i64 leaf_entries(const BandTask &t, int tiles)
+{
+    const bool tile = tiles && tile_ring_for(t.mat_cs) <= kTileMaxRing;          // mat_cs = band height of a warp-class leaf
+    return tile ? 2 * (i64)((t.n + 63) / 64) * t.mat_cs : (i64)(t.n + 1) * t.mat_cs;
+}
+__global__ void k_chunk_end_leaves(const BandTask *leaves, const int *list, int n, int s, i64 limit, int *out, i64 *start_off, i64 *ent, int tiles)
 {
     const i64 base = leaves[list[s]].mat_off;
     int lo = s + 1, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         const BandTask &t = leaves[list[mid - 1]];
-        if (t.mat_off + (i64)(t.n + 1) * t.mat_cs - base <= limit) lo = mid; else hi = mid - 1;
+        if (t.mat_off + leaf_entries(t, tiles) - base <= limit) lo = mid; else hi = mid - 1;
     }
     out[0] = lo; start_off[0] = base;
+    const BandTask &t = leaves[list[lo - 1]];
+    ent[0] = t.mat_off + leaf_entries(t, tiles) - base;
 }
 
 struct RunPlan {
     PlanSum tot;          // totals of the fast path
     i64 mat_t = 0;        // entries of the thread-kernel groups
     int n_groups = 0;
+    unsigned tile_mask = 0;   // band-height classes of the tile leaves; bit 31: some warp-class leaf needs the full matrix
 };
 
 }  // namespace
@@ -384,6 +536,7 @@ int qb200_create(qb200_ctx_t **out, int device)
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return QB200_ERR_CUDA; }
     ctx->own_stream = true;
+    if (const char *e = getenv("QB200_TILES")) ctx->use_tiles = atoi(e) != 0;
     *out = ctx;
     return 0;
 }
@@ -400,7 +553,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
                       &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
                       &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB, &ctx->d_peq2, &ctx->d_jobs2, &ctx->d_tasks2, &ctx->d_wintasks,
-                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter})
+                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter, &ctx->d_tclass, &ctx->d_tctl, &ctx->d_punt, &ctx->d_gather})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     ctx->h_pairs.release();
@@ -651,9 +804,11 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         pp.algo = (int)prm.algo; pp.bandwidth = prm.bandwidth; pp.hew_pct0 = prm.hew_percentage[0];
         pp.only_score = prm.only_score; pp.thread_band_max = kThreadBandMax;
         pp.ok_status = (prm.algo == HIRSCHBERG) ? QUICKED_OK : QUICKED_WIP;
+        pp.tiles = ctx->use_tiles ? 1 : 0;
         k_plan<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, pp, ctx->d_bound.as<int>(), ctx->d_hew.as<int>(),
                                                ctx->d_plan_items.as<PlanSum>(), ctx->d_cls.as<unsigned char>(), ctx->d_cutoff.as<i64>(),
-                                               ctx->d_status.as<int>(), ctx->d_score.as<int>(), use_fused ? ctx->d_done.as<unsigned char>() : nullptr);
+                                               ctx->d_status.as<int>(), ctx->d_score.as<int>(), use_fused ? ctx->d_done.as<unsigned char>() : nullptr,
+                                               reinterpret_cast<unsigned *>(ctx->d_counters.as<u64>() + 28));
         CK(cudaGetLastError());
         size_t tmp = 0;
         const PlanSum zero = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -664,8 +819,10 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         CK(cudaGetLastError());
         ctx->stats.kernel_launches += 4;
         CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_plan_offs.as<PlanSum>() + n, sizeof(PlanSum), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 192, ctx->d_counters.as<u64>() + 28, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         plan.tot = *reinterpret_cast<PlanSum *>(ctx->h_pinned);
+        plan.tile_mask = *reinterpret_cast<unsigned *>(ctx->h_pinned + 192);
     }
     const PlanSum &tot = plan.tot;
 
@@ -733,41 +890,80 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, std::max(ctx->d_matrix.cap, (size_t)((free_b + ctx->d_matrix.cap) * 0.85))) / 16);
         if (need <= limit) {
             CK(ctx->d_matrix.reserve((size_t)need * 16));
+            const bool tiles = ctx->use_tiles && (plan.tile_mask & 0xffu);
+            const bool wide = !ctx->use_tiles || (plan.tile_mask >> 31);          // leaves for the full-matrix warp kernels
+            const int min_B = ctx->use_tiles ? kTileBandMax + 1 : 0;
             {
                 Span sp(ctx, ST_FILL);
                 int rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), 0, (int)tot.t, 0);
-                if (!rc) rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0);
+                if (!rc && tiles) rc = launch_tiles<true>(ctx, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, ctx->d_peq.as<u64>(), plan.tile_mask & 0xffu);
+                if (!rc && wide) rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, nullptr, min_B);
                 if (rc) return rc;
             }
             {
                 Span sp(ctx, ST_TRACE);
                 int rc = launch_traceback(ctx, ctx->d_list_t.as<int>(), 0, (int)tot.t, 0, false);
-                if (!rc) rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, true);
+                if (!rc && tiles) rc = launch_tile_traceback(ctx, ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, ctx->d_peq.as<u64>());
+                if (!rc && wide) rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, true, min_B);
                 if (rc) return rc;
             }
             ctx->stats.matrix_bytes += need * 16;
+            if (tiles) { int rc = rerun_punted_leaves(ctx, ctx->d_peq.as<u64>()); if (rc) return rc; }
         } else {
             CK(ctx->d_matrix.reserve((size_t)limit * 16));
             int *d_idx = reinterpret_cast<int *>(ctx->d_counters.as<u64>() + 20);
+            i64 *d_ent = reinterpret_cast<i64 *>(ctx->d_counters.as<u64>() + 21);
             i64 *d_off = reinterpret_cast<i64 *>(ctx->d_counters.as<u64>() + 22);
+            // a single leaf / thread group can be larger than the pool limit: grow the pool for that chunk if the device
+            // has the memory, fail with QB200_ERR_OOM otherwise (never launch a fill past the end of the pool)
+            auto fit_chunk = [&](i64 ent) -> int {
+                if ((size_t)ent * 16 <= ctx->d_matrix.cap) return 0;
+                size_t fb = 0, tb = 0;
+                if (cudaMemGetInfo(&fb, &tb) != cudaSuccess) { (void)cudaGetLastError(); fb = 0; }
+                if ((size_t)ent * 16 > (size_t)((fb + ctx->d_matrix.cap) * 0.95)) {
+                    ctx->err = "a single traceback matrix (" + std::to_string((long long)ent * 16) + " bytes) does not fit the workspace";
+                    return QB200_ERR_OOM;
+                }
+                cudaError_t e = ctx->d_matrix.reserve((size_t)ent * 16);
+                if (e != cudaSuccess) { (void)cudaGetLastError(); ctx->err = "out of device memory for a single traceback matrix"; return QB200_ERR_OOM; }
+                return 0;
+            };
             // warp-kernel leaves
+            const bool tiles = ctx->use_tiles && (plan.tile_mask & 0xffu);
+            const bool wide = !ctx->use_tiles || (plan.tile_mask >> 31);
+            const int min_B = ctx->use_tiles ? kTileBandMax + 1 : 0;
             for (int s0 = 0; s0 < (int)tot.w;) {
-                k_chunk_end_leaves<<<1, 1, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), (int)tot.w, s0, limit, d_idx, d_off);
+                k_chunk_end_leaves<<<1, 1, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), (int)tot.w, s0, limit, d_idx, d_off, d_ent, ctx->use_tiles ? 1 : 0);
                 CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 24, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
                 const int s1 = *reinterpret_cast<int *>(ctx->h_pinned);
                 const i64 sub = *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
-                { Span sp(ctx, ST_FILL); int rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub); if (rc) return rc; }
-                { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub, true); if (rc) return rc; }
+                { const int rc = fit_chunk(*reinterpret_cast<i64 *>(ctx->h_pinned + 8)); if (rc) return rc; }
+                {
+                    Span sp(ctx, ST_FILL);
+                    int rc = 0;
+                    if (tiles) rc = launch_tiles<true>(ctx, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub, ctx->d_peq.as<u64>(), plan.tile_mask & 0xffu);
+                    if (!rc && wide) rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub, nullptr, min_B);
+                    if (rc) return rc;
+                }
+                {
+                    Span sp(ctx, ST_TRACE);
+                    int rc = 0;
+                    if (tiles) rc = launch_tile_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub, ctx->d_peq.as<u64>());
+                    if (!rc && wide) rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub, true, min_B);
+                    if (rc) return rc;
+                }
+                if (tiles) { int rc = rerun_punted_leaves(ctx, ctx->d_peq.as<u64>()); if (rc) return rc; }
                 s0 = s1;
             }
             // thread-kernel groups
             for (int g0 = 0; g0 < plan.n_groups;) {
-                k_chunk_end_groups<<<1, 1, 0, ctx->stream>>>(ctx->d_goff.as<i64>(), ctx->d_gsize.as<i64>(), plan.n_groups, g0, limit, d_idx);
-                CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                k_chunk_end_groups<<<1, 1, 0, ctx->stream>>>(ctx->d_goff.as<i64>(), ctx->d_gsize.as<i64>(), plan.n_groups, g0, limit, d_idx, d_ent);
+                CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 16, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaMemcpyAsync(ctx->h_pinned + 16, ctx->d_goff.as<i64>() + g0, 8, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
                 const int g1 = *reinterpret_cast<int *>(ctx->h_pinned);
+                { const int rc = fit_chunk(*reinterpret_cast<i64 *>(ctx->h_pinned + 8)); if (rc) return rc; }
                 const i64 sub = tot.matw + *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
                 const int q0 = g0 * 32, q1 = (int)std::min<i64>(tot.t, (i64)g1 * 32);
                 { Span sp(ctx, ST_FILL); int rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), q0, q1 - q0, sub); if (rc) return rc; }
@@ -882,13 +1078,16 @@ int run_score_tasks(qb200_ctx *ctx, std::vector<BandTask> &tasks, std::vector<Ba
     outs.resize(nt);
     if (!nt) return 0;
     i64 st = 0, sc = 0;
-    unsigned mask = 0;
+    unsigned mask = 0, tmask = 0;          // band-height classes for the sweep kernels / the tile kernels
     for (size_t i = 0; i < nt; ++i) {
         BandTask &t = tasks[i];
         const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
-        const int R = rounds_for(g.Bs);
-        if (!R) { ctx->err = "score-only band of " + std::to_string(g.Bs) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
-        mask |= (unsigned)R;
+        if (ctx->use_tiles && tile_band_ok(g.Bs)) tmask |= tile_class_bit(g.Bs);
+        else {
+            const int R = rounds_for(g.Bs);
+            if (!R) { ctx->err = "score-only band of " + std::to_string(g.Bs) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
+            mask |= (unsigned)R;
+        }
         t.slot = (int)i; t.state_off = st; t.scores_off = sc;
         st += 2 * g.Bs; sc += (i64)((t.m + 63) / 64) + g.Bs + 2;
     }
@@ -900,8 +1099,21 @@ int run_score_tasks(qb200_ctx *ctx, std::vector<BandTask> &tasks, std::vector<Ba
     CK(cudaMemcpyAsync(ctx->d_tasks2.p, tasks.data(), sizeof(BandTask) * nt, cudaMemcpyHostToDevice, ctx->stream));
     {
         Span sp(ctx, stage);
-        int rc = launch_banded<false>(ctx, mask, ctx->d_tasks2.as<BandTask>(), nullptr, 0, (int)nt, 0, ctx->d_peq2.as<u64>());
+        int rc = 0;
+        if (tmask) rc = launch_tiles<false>(ctx, ctx->d_tasks2.as<BandTask>(), nullptr, 0, (int)nt, 0, ctx->d_peq2.as<u64>(), tmask);
+        if (!rc && mask) rc = launch_banded<false>(ctx, mask, ctx->d_tasks2.as<BandTask>(), nullptr, 0, (int)nt, 0, ctx->d_peq2.as<u64>(),
+                                                   ctx->use_tiles ? kTileBandMax + 1 : 0);
         if (rc) return rc;
+    }
+    if (tmask) {        // passes the tile kernels gave up on (band ran empty): the sweep kernels redo them
+        CK(cudaMemcpyAsync(ctx->h_pinned + 128, &ctx->d_tctl.as<TileCtl>()->punt_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const int cnt = *reinterpret_cast<int *>(ctx->h_pinned + 128);
+        if (cnt > 0) {
+            Span sp(ctx, stage);
+            int rc = launch_banded<false>(ctx, 127u, ctx->d_tasks2.as<BandTask>(), ctx->d_punt.as<int>(), 0, cnt, 0, ctx->d_peq2.as<u64>());
+            if (rc) return rc;
+        }
     }
     CK(cudaMemcpyAsync(outs.data(), ctx->d_bandout.p, sizeof(BandOut) * nt, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -940,20 +1152,36 @@ int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, (size_t)((free_b + ctx->d_matrix.cap) * 0.85)) / 16);
-    std::vector<int> Bc(nl), list_t, list_w;
+    std::vector<int> Bc(nl), list_t, list_w, list_x;      // thread kernel / full-matrix warp kernel / tile kernels
     i64 rg = 0, sc = 0;
+    unsigned xmask = 0;
     for (size_t i = 0; i < nl; ++i) {
         BandTask &t = leaves[i];
         const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
         Bc[i] = (int)g.Bc;
         if (g.Bc > kThreadBandMax && !rounds_for(g.Bc)) { ctx->err = "leaf band of " + std::to_string(g.Bc) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
-        (g.Bc <= kThreadBandMax ? list_t : list_w).push_back((int)i);
+        if (g.Bc <= kThreadBandMax) list_t.push_back((int)i);
+        else if (ctx->use_tiles && tile_band_ok(g.Bc)) { list_x.push_back((int)i); xmask |= tile_class_bit(g.Bc); }
+        else list_w.push_back((int)i);
         t.range_off = rg; rg += t.n / 64 + 2;
         t.scores_off = sc; if (g.Bc > kThreadBandMax) sc += (i64)((t.m + 63) / 64) + g.Bc + 2;
     }
-    // chunk plans: (is_thread, list begin, list end, entries)
+    // chunk plans: (kind: 1 thread kernel, 0 warp kernel, 2 tile kernels; list begin, list end, entries)
     struct Chunk { int thr, q0, q1; i64 ent; };
     std::vector<Chunk> chunks;
+    for (size_t q0 = 0; q0 < list_x.size();) {                        // tile leaves: one 32-byte record per tile
+        i64 ent = 0; size_t q1 = q0;
+        while (q1 < list_x.size()) {
+            BandTask &t = leaves[list_x[q1]];
+            const i64 e = 2 * (i64)((t.n + 63) / 64) * Bc[list_x[q1]];
+            if (q1 > q0 && ent + e > limit) break;
+            t.mat_off = ent; t.mat_cs = Bc[list_x[q1]]; t.mat_ws = 1;
+            ent += e; ++q1;
+        }
+        if ((size_t)ent * 16 > free_b + ctx->d_matrix.cap) { ctx->err = "the tile records of a single leaf do not fit the device"; return QB200_ERR_OOM; }
+        chunks.push_back({2, (int)q0, (int)q1, ent});
+        q0 = q1;
+    }
     for (size_t g0 = 0; g0 < list_t.size();) {                       // thread-kernel groups of 32
         i64 ent = 0; size_t q0 = g0;
         while (g0 < list_t.size()) {
@@ -982,16 +1210,27 @@ int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
     }
     for (int &v : list_t) v += (int)L0;
     for (int &v : list_w) v += (int)L0;
+    for (int &v : list_x) v += (int)L0;
     CK(cudaMemcpyAsync(ctx->d_leaves.as<BandTask>() + L0, leaves.data(), sizeof(BandTask) * nl, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_list_t.reserve(list_t.size() * 4 + 16));
-    CK(ctx->d_list_w.reserve(list_w.size() * 4 + 16));
+    CK(ctx->d_list_w.reserve((list_w.size() + list_x.size()) * 4 + 16));
     CK(cudaMemcpyAsync(ctx->d_list_t.p, list_t.data(), list_t.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_list_w.p, list_w.data(), list_w.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    int *d_list_x = ctx->d_list_w.as<int>() + list_w.size();
+    CK(cudaMemcpyAsync(d_list_x, list_x.data(), list_x.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx->d_ranges.reserve((size_t)rg * 8 + 16));
     CK(ctx->d_scores.reserve((size_t)sc * 4 + 16));
     CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)sc * 4 + 16, ctx->stream));
     for (const Chunk &c : chunks) {
         CK(ctx->d_matrix.reserve((size_t)c.ent * 16));
+        if (c.thr == 2) {
+            { Span sp(ctx, ST_FILL); int rc = launch_tiles<true>(ctx, ctx->d_leaves.as<BandTask>(), d_list_x, c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>(), xmask); if (rc) return rc; }
+            { Span sp(ctx, ST_TRACE); int rc = launch_tile_traceback(ctx, d_list_x, c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>()); if (rc) return rc; }
+            ctx->stats.matrix_bytes += c.ent * 16;
+            int rc = rerun_punted_leaves(ctx, ctx->d_peq2.as<u64>());       // synchronises
+            if (rc) return rc;
+            continue;
+        }
         const int *lst = c.thr ? ctx->d_list_t.as<int>() : ctx->d_list_w.as<int>();
         {
             Span sp(ctx, ST_FILL);
@@ -1284,7 +1523,10 @@ static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std:
             lf.p_off = nd.p_off; lf.t_off = nd.t_off; lf.m = nd.m; lf.n = nd.n; lf.rev = 0; lf.finish = nd.n; lf.cutoff = nd.cutoff;
             lf.nbp = (nd.m + 63) / 64 + 2; lf.pair = slow_pairs[q];
             lf.ops_cap = ((nd.m + nd.n + 15) / 16) * 16; lf.ops_off = ops_words;
-            ops_words += (band_geometry(nd.m, nd.n, nd.cutoff).Bc <= kThreadBandMax) ? lf.ops_cap / 16 : lf.ops_cap;   // u32 runs for warp walks
+            {   // 2-bit ops (thread walk, tile walk); u32 runs, worst case, for the full-matrix warp walk
+                const i64 bc = band_geometry(nd.m, nd.n, nd.cutoff).Bc;
+                ops_words += (bc <= kThreadBandMax || (ctx->use_tiles && tile_band_ok(bc))) ? lf.ops_cap / 16 : lf.ops_cap;
+            }
             lf.slot = (int)(L0 + (i64)leaves.size());
             if (res[q].pl.n_leaves == 0) res[q].pl.first_leaf = lf.slot;
             res[q].pl.n_leaves++;
@@ -1570,7 +1812,7 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
             acc.banded_tries += st.banded_tries; acc.hirschberg_splits += st.hirschberg_splits; acc.leaves += st.leaves;
             acc.ms_total += st.ms_total; acc.ms_prepare += st.ms_prepare; acc.ms_windowed_s += st.ms_windowed_s; acc.ms_windowed_l += st.ms_windowed_l;
             acc.ms_banded += st.ms_banded; acc.ms_align_fill += st.ms_align_fill; acc.ms_align_trace += st.ms_align_trace; acc.ms_cigar += st.ms_cigar;
-            acc.matrix_bytes += st.matrix_bytes; acc.ms_fused += st.ms_fused; acc.pairs_fused += st.pairs_fused;
+            acc.matrix_bytes += st.matrix_bytes; acc.ms_fused += st.ms_fused; acc.pairs_fused += st.pairs_fused; acc.leaves_punted += st.leaves_punted;
             if (trace) fprintf(stderr, "[qb200 pipeline] sub %d downloaded in %.2f ms\n", k, t_ms(t0));
             { std::lock_guard<std::mutex> lk(mu); downloaded = k + 1; }
             cv.notify_all();

@@ -7,6 +7,7 @@
 #pragma once
 #include "qb_common.cuh"
 #include "qb_traceback.cuh"
+#include "qb_tiles.cuh"
 
 namespace qb {
 
@@ -38,6 +39,7 @@ struct PlanParams {
     int only_score;
     int thread_band_max;    // B_cigar <= this -> thread kernel
     int ok_status;          // QUICKED_WIP or QUICKED_OK (HIRSCHBERG)
+    int tiles;              // wider bands: tile records + tile traceback (qb_tiles.cuh) instead of the full matrix
 };
 
 __device__ __forceinline__ int rounds_for_dev(i64 B)
@@ -48,7 +50,8 @@ __device__ __forceinline__ int rounds_for_dev(i64 B)
 __global__ void __launch_bounds__(256)
 k_plan(const PairRec *__restrict__ pairs, int n, PlanParams pp, const int *__restrict__ bound,
        const int *__restrict__ hew, PlanSum *__restrict__ items, unsigned char *__restrict__ cls,
-       i64 *__restrict__ cutoff, int *__restrict__ status, int *__restrict__ score, const unsigned char *__restrict__ done)
+       i64 *__restrict__ cutoff, int *__restrict__ status, int *__restrict__ score, const unsigned char *__restrict__ done,
+       unsigned *__restrict__ tile_class_mask)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -85,9 +88,20 @@ k_plan(const PairRec *__restrict__ pairs, int n, PlanParams pp, const int *__res
                 c = thr ? CLS_T : CLS_W;
                 st = pp.ok_status;
                 it.leaf = 1; it.t = thr; it.w = !thr;
-                it.ops = thr ? (r.m + r.n + 15) / 16 : (r.m + r.n + 15) / 16 * 16;  // 2-bit ops (thread walk) / u32 runs, worst case (warp walk)
+                const bool tile = !thr && pp.tiles && tile_ring_for(g.Bc) <= kTileMaxRing;
+                // 2-bit ops (thread walk, tile walk) / u32 runs, worst case (warp walk)
+                it.ops = (thr || tile) ? (r.m + r.n + 15) / 16 : (r.m + r.n + 15) / 16 * 16;
                 it.rng = r.n / 64 + 2;
-                if (!thr) { it.sc = (r.m + 63) / 64 + g.Bc + 2; it.matw = (i64)(r.n + 1) * g.Bc; }
+                if (!thr) {
+                    it.sc = (r.m + 63) / 64 + g.Bc + 2;
+                    // traceback state in 16-byte units: one 32-byte record per tile, or the reference's whole matrix
+                    it.matw = tile ? 2 * (i64)((r.n + 63) / 64) * g.Bc : (i64)(r.n + 1) * g.Bc;
+                    if (tile) {
+                        int cb = 0;
+                        while ((8 << cb) < tile_ring_for(g.Bc)) ++cb;
+                        atomicOr(tile_class_mask, 1u << cb);
+                    } else atomicOr(tile_class_mask, 1u << 31);      // some leaf needs the full-matrix warp kernels
+                }
             }
         }
     }

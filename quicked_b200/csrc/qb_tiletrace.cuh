@@ -1,0 +1,141 @@
+// qb_tiletrace.cuh — BandEd traceback over TILE RECORDS (reference walk: bpm_banded.c:967-1036).
+//
+// The reference walks a stored (n+1) x B matrix of (Pv,Mv) words (bpm_banded.c:139-140).  The tile fill
+// (qb_tiles.cuh) stores, per 64x64 tile, only the block's (Pv,Mv) at the tile's first column and the 64 carry-in
+// pairs (32 bytes).  A tile's 64 columns are a pure function of that record, the block's five match masks and 64
+// text codes, so the walk recomputes exactly the tiles it visits — about 1.5 per 64 columns instead of the band's
+// whole height — and never reads more than 32 bytes of traceback state per tile from HBM.
+//
+// ONE LEAF PER THREAD.  For the tile the walk is in, the thread recomputes the columns from the tile's first up to the
+// walk's column and keeps, per column, the walk's DECISION for the 16 rows around the walk's diagonal as two bit planes
+// in one u32 of shared memory (the walk can only leave its diagonal through an insertion or a deletion):
+//     a = Pv[c+1] | ~(Mv[c] | Eq[c]),  b = ~Pv[c+1] & (Mv[c] | ~Eq[c])
+//     (a,b) = (1,0) deletion, (0,1) insertion, (1,1) mismatch, (0,0) match
+// which is the reference's test order: D if Pv[col h+1] bit v, else I if Mv[col h] bit v, else M/X (:1002-1023).
+// M/X come from the match masks; a cell whose row or column holds a character outside "ACGTN" (where equal codes do
+// not imply equal bytes) compares the RAW bytes like the reference (:1012).  When the walk drifts out of the 16-row
+// slice the tile is recomputed around the walk's current cell.
+//
+// The walk PUNTS (returns non-zero, nothing written is used) as soon as it would read a cell outside the live band
+// of its column block, or the first-row word of a block the lower cut has just dropped: there the reference reads
+// stale or never-written words (too-narrow bands) and the exact full-matrix kernels
+// (qb_banded.cuh + qb_traceback.cuh) redo the leaf.
+#pragma once
+#include "qb_tiles.cuh"
+#include "qb_traceback.cuh"
+
+namespace qb {
+
+constexpr int kTraceCols = 64;        // plane words per thread (one per tile column)
+constexpr int kTraceHalf = 8;         // rows kept on each side of the walk's diagonal
+
+// planes[s * ps]: decision planes of tile column s; eq[c * eqs]: the block's match masks.
+QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ranges, const unsigned char *codes,
+                         const unsigned char *raw, const u64 *peq_pool, u32 *ops, u32 *planes, int ps, u64 *eq, int eqs,
+                         LeafOut &o)
+{
+    const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
+    const int B = (int)g.Bc, prolog = (int)g.prolog;
+    const int nshift = tk.n >> 6;
+    const u64 *pq = peq_pool + tk.peq_off;
+    const unsigned char *tcodes = codes + tk.t_off;
+    const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
+    OpWriter w; w.init(ops, tk.ops_cap);
+    int h = tk.n - 1, v = tk.m - 1;
+    int eq_block = -1;
+    u64 rowodd = 0;
+    while (v >= 0 && h >= 0) {
+        const int kb = h >> 6, b = v >> 6;
+        const int j = b - (kb - prolog);
+        const int2 rg = ranges[kb];
+        if (j < rg.x || j > rg.y) return 1;                          // outside the live band of this column block
+        const int s0 = h & 63, r0 = v & 63;
+        if (s0 == 63) {
+            // Pv[col 64(kb+1)] lives in the NEXT block's coordinates (stored after the shift, bpm_banded.c:279-287):
+            // word j-1 there, which the reference only wrote from the new `first` on
+            if (kb + 1 > nshift || j - 1 < ranges[kb + 1].x) return 2;
+        }
+        if (b != eq_block) {
+#pragma unroll
+            for (int c = 0; c < kAlpha; ++c) eq[c * eqs] = pq[(i64)b * kPeqStride + c];
+            rowodd = pq[(i64)b * kPeqStride + kAlpha];
+            eq_block = b;
+        }
+        // ---- recompute columns 0..s0 of tile (j, kb) ----
+        const TileRec rec = recs[(i64)kb * B + j];
+        u64 pv = rec.pv0, mv = rec.mv0;
+        const int lo0 = r0 - s0 - kTraceHalf;                        // lowest slice row at column 0 (may be negative)
+        u64 colodd = 0;                                              // columns whose text character is outside "ACGTN"
+#pragma unroll 1
+        for (int s = 0; s <= s0; ++s) {
+            const unsigned cs = tcodes[64 * kb + s];
+            const u64 e = eq[(cs & 7u) * eqs];
+            colodd |= (u64)((cs >> 3) & 1u) << s;
+            const u32 hp = ((s < 32 ? rec.cin.p0 : rec.cin.p1) >> (31 - (s & 31))) & 1u;
+            const u32 hm = ((s < 32 ? rec.cin.m0 : rec.cin.m1) >> (31 - (s & 31))) & 1u;
+            const u64 mv_old = mv;
+            u32 d0, d1;
+            myers_step(e, pv, mv, hp, hm, d0, d1);
+            const u64 pa = pv | ~(mv_old | e), pb = ~pv & (mv_old | ~e);
+            const int lo = lo0 + s;
+            u32 sa, sb;
+            if (lo >= 0) { sa = lo < 64 ? (u32)(pa >> lo) : 0u; sb = lo < 64 ? (u32)(pb >> lo) : 0u; }
+            else { sa = -lo < 64 ? (u32)(pa << -lo) : 0u; sb = -lo < 64 ? (u32)(pb << -lo) : 0u; }
+            planes[s * ps] = (sa & 0xffffu) | (sb << 16);
+        }
+        // ---- walk inside the tile ----
+        int r = r0, s = s0;
+        for (;;) {
+            if (r < 0 || s < 0) break;                               // left the tile through its top / left edge
+            const int q = (r - r0) + (s0 - s) + kTraceHalf;
+            if (q < 0 || q > 15) break;                              // drifted out of the slice: recompute around (r, s)
+            const u32 wd = planes[s * ps];
+            const u32 a = (wd >> q) & 1u, bb = (wd >> (16 + q)) & 1u;
+            int op;
+            if (a != bb) op = a ? OP_D : OP_I;
+            else {
+                op = a ? OP_X : OP_M;
+                if (((rowodd >> r) | (colodd >> s)) & 1ull)           // odd character: raw bytes decide (bpm_banded.c:1012)
+                    op = (traw[64 * kb + s] == praw[64 * b + r]) ? OP_M : OP_X;
+            }
+            w.emit(op);
+            r -= (op != OP_I) ? 1 : 0;
+            s -= (op != OP_D) ? 1 : 0;
+        }
+        v = 64 * b + r;
+        h = 64 * kb + s;
+    }
+    while (h >= 0) { w.emit(OP_I); --h; }
+    while (v >= 0) { w.emit(OP_D); --v; }
+    w.finish();
+    o.n_ops = tk.ops_cap - w.pos; o.cost = w.cost; o.text_len = w.text_len; o.fmt = 0; o.pad_ = 0;
+    return 0;
+}
+
+#ifdef __CUDACC__
+// One leaf per thread; leaves that punt are appended to punt_list for the exact kernels.
+constexpr int kTileTraceThreads = 128;
+__global__ void __launch_bounds__(kTileTraceThreads)
+k_traceback_tiles(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 rec_sub,
+                  const unsigned char *__restrict__ codes, const unsigned char *__restrict__ raw, const u64 *__restrict__ peq,
+                  const TileRec *__restrict__ recs, const int2 *__restrict__ range_pool, const BandOut *__restrict__ fill_out,
+                  u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs, int *__restrict__ punt_list, int *__restrict__ punt_count)
+{
+    __shared__ u32 s_planes[kTraceCols * kTileTraceThreads];
+    __shared__ u64 s_eq[kAlpha * kTileTraceThreads];
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_tasks) return;
+    const int ti = list ? list[begin + id] : begin + id;
+    const BandTask tk = tasks[ti];
+    if (tile_ring_for(band_geometry(tk.m, tk.n, tk.cutoff).Bc) > kTileMaxRing) return;   // full-matrix leaf (warp kernels)
+    LeafOut o;
+    int rc = 3;
+    if (fill_out[tk.slot].pos_v != kTilePunted)
+        rc = tile_traceback(tk, recs + (tk.mat_off - rec_sub) / 2, range_pool + tk.range_off, codes, raw, peq, ops_pool + tk.ops_off,
+                            s_planes + threadIdx.x, kTileTraceThreads, s_eq + threadIdx.x, kTileTraceThreads, o);
+    if (rc) { punt_list[atomicAdd(punt_count, 1)] = ti; return; }
+    outs[tk.slot] = o;
+}
+#endif
+
+}  // namespace qb

@@ -19,8 +19,8 @@ struct OpWriter {
     int pos;        // next op goes to pos-1
     u32 acc;
     int cost, text_len, cur_op, cur_len;
-    __device__ __forceinline__ void init(u32 *w, int cap) { words = w; pos = cap; acc = 0; cost = 0; text_len = 0; cur_op = -1; cur_len = 0; }
-    __device__ __forceinline__ void emit(int op)
+    __host__ __device__ __forceinline__ void init(u32 *w, int cap) { words = w; pos = cap; acc = 0; cost = 0; text_len = 0; cur_op = -1; cur_len = 0; }
+    __host__ __device__ __forceinline__ void emit(int op)
     {
         --pos;
         acc |= (u32)op << (2 * (pos & 15));
@@ -32,7 +32,7 @@ struct OpWriter {
             cur_op = op; cur_len = 1;
         }
     }
-    __device__ __forceinline__ void finish()
+    __host__ __device__ __forceinline__ void finish()
     {
         if (pos & 15) words[pos >> 4] = acc;
         if (cur_len) text_len += dec_digits((unsigned)cur_len) + 1;
@@ -169,7 +169,7 @@ constexpr int kTraceWarpsPerCta = 4;
 __global__ void __launch_bounds__(32 * kTraceWarpsPerCta)
 k_traceback_warp(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
                  const unsigned char *__restrict__ raw, const ulonglong2 *__restrict__ matrix,
-                 const int2 *__restrict__ range_pool, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs)
+                 const int2 *__restrict__ range_pool, u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs, int min_B)
 {
     __shared__ ulonglong2 s_tile[kTraceWarpsPerCta][32][2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -179,6 +179,7 @@ k_traceback_warp(const BandTask *__restrict__ tasks, const int *__restrict__ lis
     tk.mat_off -= mat_sub;
     const BandGeom g = band_geometry(tk.m, tk.n, tk.cutoff);
     const int B = (int)g.Bc, prolog = (int)g.prolog;
+    if (B < min_B) return;                   // narrower bands were walked by the tile traceback
     const ulonglong2 *mat = matrix + tk.mat_off;
     const int2 *ranges = range_pool + tk.range_off;
     const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;

@@ -46,6 +46,7 @@ struct BandTask {
     i64 range_off;        // leaf: int2 index of the per-column-block live range (first,last) of the band
     int ops_cap;          // leaf: capacity in ops (= m+n rounded up to 16)
     int slot;             // free for the scheduler (e.g. node id in the Hirschberg tree)
+    i64 tt_off;           // tile kernels: u64 index of this task's aligned text codes in the tile-text pool (set on the device)
 };
 
 // Result of a BandEd pass.

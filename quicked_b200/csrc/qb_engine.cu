@@ -124,7 +124,7 @@ struct qb200_ctx {
     int max_n = 0, max_m = 0;
     int ws_carve_set[2][2] = {{-1, -1}, {-1, -1}};   // shared-memory carve-out already requested for each WindowEd(S) kernel variant
     int sms = 0;                           // SM count of the device (queried once)
-    DevBuf d_tclass, d_tctl, d_punt, d_gather;   // tile path: per-class task lists, counters, punted tasks
+    DevBuf d_tclass, d_tctl, d_punt, d_gather, d_ttext;   // tile path: per-class task lists, counters, punted tasks
     bool use_tiles = true;
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
@@ -339,7 +339,7 @@ int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, 
 
 // ---- tile path (qb_tiles.cuh / qb_tiletrace.cuh) ----------------------------------------------------------------
 constexpr int kTileClasses = 8;                     // ring sizes 8 << c: bands up to kTileMaxRing - 2 blocks
-struct TileCtl { int counts[kTileClasses]; int next[kTileClasses]; int punt_count; int pad_[15]; };
+struct TileCtl { int counts[kTileClasses]; int next[kTileClasses]; int punt_count; int pad_; unsigned long long tt_words; int pad2_[12]; };
 inline bool tile_band_ok(i64 B) { return tile_ring_for(B) <= kTileMaxRing; }
 
 template <bool FULL, int LANES>
@@ -347,7 +347,8 @@ int launch_tiles_class(qb200_ctx *ctx, const TilePools &P, int c, int cap, int n
 {
     const int RB = 8 << c;
     const size_t fixed = tile_smem_bytes(RB, 0, LANES), per = tile_slot_arena_bytes(RB) + sizeof(TileSlot);
-    const size_t budget = (RB <= 128 ? 72 : 110) * 1024;
+    size_t budget = (RB <= 128 ? 55 : 110) * 1024;           // <= 128 blocks: four CTAs per SM
+    if (const char *e = getenv("QB200_TILE_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
     int nslots = (int)((budget > fixed ? budget - fixed : 0) / per);
     nslots = std::max(1, std::min(32, nslots));
     if (const char *e = getenv("QB200_TILE_SLOTS")) nslots = std::max(1, std::min(32, atoi(e)));
@@ -372,18 +373,24 @@ int launch_tiles_class(qb200_ctx *ctx, const TilePools &P, int c, int cap, int n
 // FULL: writes tile records (pool d_matrix, task.mat_off in 16-byte units) + live ranges; !FULL: score-only passes.
 // Tasks the kernels give up on: FULL -> BandOut.pos_v = kTilePunted; !FULL -> appended to d_punt (count in d_tctl).
 template <bool FULL>
-int launch_tiles(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base,
+int launch_tiles(qb200_ctx *ctx, BandTask *d_tasks, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base,
                  unsigned class_mask = 0xffu)
 {
     if (n <= 0) return 0;
     CK(ctx->d_tclass.reserve((size_t)kTileClasses * (size_t)n * 4));
     CK(ctx->d_tctl.reserve(sizeof(TileCtl)));
     CK(ctx->d_punt.reserve((size_t)n * 4 + 16));
+    // tile-text pool: every task's text once more, aligned (the tasks of one launch are distinct (sub-)texts of the batch,
+    // forward and reverse pass of a Hirschberg node at most; 80 bytes of rounding per task)
+    CK(ctx->d_ttext.reserve(2 * (size_t)ctx->raw_bytes + (size_t)n * 80 + 64));
     CK(cudaMemsetAsync(ctx->d_tctl.p, 0, sizeof(TileCtl), ctx->stream));
-    k_tile_classes<FULL><<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_tclass.as<int>(), n, ctx->d_tctl.as<TileCtl>()->counts);
+    k_tile_classes<FULL><<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_tclass.as<int>(), n, ctx->d_tctl.as<TileCtl>()->counts,
+                                                                  &ctx->d_tctl.as<TileCtl>()->tt_words);
+    k_tile_text<FULL><<<(int)(((i64)n * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_codes.as<unsigned char>(), ctx->d_ttext.as<u64>());
     CK(cudaGetLastError());
-    ctx->stats.kernel_launches++;
+    ctx->stats.kernel_launches += 2;
     TilePools P;
+    P.ttext = ctx->d_ttext.as<u64>();
     P.tasks = d_tasks; P.codes = ctx->d_codes.as<unsigned char>(); P.peq = peq_base; P.recs = ctx->d_matrix.as<TileRec>();
     P.ranges = ctx->d_ranges.as<int2>(); P.scores = ctx->d_scores.as<int>(); P.state = ctx->d_state.as<u64>();
     P.outs = ctx->d_bandout.as<BandOut>(); P.punt_list = ctx->d_punt.as<int>(); P.punt_count = &ctx->d_tctl.as<TileCtl>()->punt_count;
@@ -391,9 +398,11 @@ int launch_tiles(qb200_ctx *ctx, const BandTask *d_tasks, const int *d_list, int
     for (int c = 0; c < kTileClasses; ++c) {
         if (!((class_mask >> c) & 1u)) continue;
         int rc;
-        if (c == 0) rc = launch_tiles_class<FULL, 32>(ctx, P, c, n, n);
-        else if (c == 1) rc = launch_tiles_class<FULL, 64>(ctx, P, c, n, n);
-        else rc = launch_tiles_class<FULL, 128>(ctx, P, c, n, n);
+        int lanes = c == 0 ? 32 : c == 1 ? 64 : 128;
+        if (const char *e = getenv("QB200_TILE_LANES")) lanes = atoi(e);
+        if (lanes == 32) rc = launch_tiles_class<FULL, 32>(ctx, P, c, n, n);
+        else if (lanes == 128) rc = launch_tiles_class<FULL, 128>(ctx, P, c, n, n);
+        else rc = launch_tiles_class<FULL, 64>(ctx, P, c, n, n);
         if (rc) return rc;
     }
     return 0;
@@ -553,7 +562,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
                       &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
                       &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB, &ctx->d_peq2, &ctx->d_jobs2, &ctx->d_tasks2, &ctx->d_wintasks,
-                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter, &ctx->d_tclass, &ctx->d_tctl, &ctx->d_punt, &ctx->d_gather})
+                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter, &ctx->d_tclass, &ctx->d_tctl, &ctx->d_punt, &ctx->d_gather, &ctx->d_ttext})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     ctx->h_pairs.release();
@@ -1032,6 +1041,13 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     // ---- stats ----
     u64 counters[4];
     memcpy(counters, ctx->h_pinned + 64, 32);
+    if (getenv("QB200_TILE_DEBUG")) {
+        u64 c[16];
+        cudaMemcpy(c, ctx->d_counters.p, 128, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[qb200 tiles] sched cycles %llu of %llu (%.1f%%), passes %llu, %.0f cycles/pass, %.0f sched cycles/pass\n", (unsigned long long)c[8],
+                (unsigned long long)c[9], c[9] ? 100.0 * c[8] / c[9] : 0.0, (unsigned long long)c[10], c[10] ? (double)c[9] / c[10] : 0.0,
+                c[10] ? (double)c[8] / c[10] : 0.0);
+    }
     ctx->stats.word_steps_windowed = (i64)counters[0];
     ctx->stats.word_steps_banded = (i64)counters[1];
     ctx->stats.word_steps = (i64)(counters[0] + counters[1]);

@@ -62,53 +62,57 @@ struct TileCarry { u32 p0, p1, m0, m1; };
 // One tile record of FULL mode (32 bytes): state of the block when the tile starts + its carry-ins.
 struct TileRec { u64 pv0, mv0; TileCarry cin; };
 
-// Ring sizes of a launch: RB block slots (power of two >= B+2), RK = 2*RB column-block slots.
+// Ring size of a launch: RB block slots = RK column-block slots (power of two >= B+2).
 QB_HD int tile_ring_for(i64 B)
 {
     int r = 8;
     while (r < B + 2) r <<= 1;
     return r;
 }
-constexpr int kTileMaxRing = 1024;
-constexpr int kTilePunted = -2147483647 - 1;   // BandOut.pos_v of a FULL-mode task the tile fill gave up on             // bands up to 1022 blocks; taller ones use the shared-memory sweep kernel
+constexpr int kTileMaxRing = 1024;             // bands up to 1022 blocks; taller ones use the shared-memory sweep kernel
+constexpr int kTilePunted = -2147483647 - 1;   // BandOut.pos_v of a FULL-mode task the tile fill gave up on
 
-// Per-slot bookkeeping (shared memory).
+// Per-slot bookkeeping.  The scheduler lane keeps its slot in registers; compute lanes read the shared-memory copy
+// (static fields written when the task is loaded, rho / kb refreshed every pass).
 struct TileSlot {
     int task;                 // index into the task array, -1: empty
     int m, n, ncols, K, nshift;
     int nblk, mmod, clamp, prolog, B, rev, nbp, out_slot;
-    i64 fin, kcut;
-    i64 peq_off, t_off, rec_off, scores_off, state_off, range_off;
+    int fin, kcut;            // band geometry (fits 32 bits: longer sequences are punted to the sweep kernels)
+    i64 peq_off, t_off, rec_off, scores_off, state_off, range_off, tt_off;
     // dynamic
-    int rho;                  // next round
+    int rho;                  // round being run / to run next
     int kt, kb;               // top[] / bot[] decided for column blocks <= kt / <= kb
     int kmin, kmax;           // tiles of round rho: column blocks kmin..kmax, block = rho - base[k]
     int cnt;                  // number of those tiles
     int state;                // 0 running, 1 finished, 2 punt (task handed to the exact fallback kernels)
     int koff;                 // tiles of the round already dispatched (a round may be spread over several passes)
+    // ring values the scheduler needs every pass, mirrored in registers
+    int c_top_t, c_base_t;                        // top[kt], base[kt]
+    int c_top_b, c_bot_b, c_base_b, c_top_b1;     // top[kb], bot[kb], base[kb], top[kb+1] (valid once kt > kb)
     u64 ws;                   // word-steps of the task (reference schedule)
 };
 
 // Views of one slot's rings inside the CTA's arena.
 struct TileRings {
-    u64 *pv, *mv;             // [RB]
-    TileCarry *carry;         // [2][RB] by round parity
+    u64 *pv, *mv;             // [RB] state of the live blocks
+    TileCarry *carry;         // [RB] carry-outs of a block's latest tile (read by the tile below BEFORE the mid-pass barrier)
     int *sc;                  // [2][RB] by column-block parity: running score after column block k
-    int *top, *bot, *base;    // [RK]
-    int RB, RK;
+    int *top, *bot, *base;    // [RB] by column block
+    int RB;
 };
-QB_HD size_t tile_slot_arena_bytes(int RB) { return (size_t)RB * (8 + 8 + 32 + 8) + (size_t)(2 * RB) * 12; }
+QB_HD size_t tile_slot_arena_bytes(int RB) { return (size_t)RB * (8 + 8 + 16 + 8 + 12); }
 QB_HD TileRings tile_rings(unsigned char *arena, int RB)
 {
     TileRings r;
-    r.RB = RB; r.RK = 2 * RB;
+    r.RB = RB;
     r.pv = reinterpret_cast<u64 *>(arena);
     r.mv = r.pv + RB;
     r.carry = reinterpret_cast<TileCarry *>(r.mv + RB);
-    r.sc = reinterpret_cast<int *>(r.carry + 2 * RB);
+    r.sc = reinterpret_cast<int *>(r.carry + RB);
     r.top = r.sc + 2 * RB;
-    r.bot = r.top + r.RK;
-    r.base = r.bot + r.RK;
+    r.bot = r.top + RB;
+    r.base = r.bot + RB;
     return r;
 }
 
@@ -117,6 +121,7 @@ struct TilePools {
     const BandTask *tasks;
     const unsigned char *codes;     // base codes of the packed batch (bit 3 = odd-character flag, masked here)
     const u64 *peq;
+    const u64 *ttext;               // per-task text codes, 8 per u64 in column order (reversed passes stored reversed), see k_tile_text
     TileRec *recs;                  // FULL: records, index rec_off + k*B + j  (j = band-relative word)
     int2 *ranges;                   // FULL: live range (first,last) per column block
     int *scores;                    // per-task running scores by absolute block (reference scores[])
@@ -138,13 +143,16 @@ QB_HD void tile_slot_load(TileSlot &S, const TileRings &R, const BandTask &tk, i
     S.clamp = FULL ? S.nblk - 1 : S.nblk;                           // bpm_banded.c:295 vs :917
     S.prolog = (int)g.prolog; S.B = (int)(FULL ? g.Bc : g.Bs);
     S.rev = tk.rev; S.nbp = tk.nbp; S.out_slot = tk.slot;
-    S.fin = g.fin; S.kcut = g.k;
+    S.fin = (int)g.fin; S.kcut = (int)g.k;
     S.peq_off = tk.peq_off; S.t_off = tk.t_off; S.rec_off = (tk.mat_off - P.rec_sub) / 2; S.scores_off = tk.scores_off;
-    S.state_off = tk.state_off; S.range_off = tk.range_off;
+    S.state_off = tk.state_off; S.range_off = tk.range_off; S.tt_off = tk.tt_off;
     S.rho = 0; S.kt = 0; S.kb = 0; S.kmin = 0; S.kmax = -1; S.cnt = 0; S.state = 0; S.koff = 0; S.ws = 0;
     R.top[0] = 0;                                                   // first + pos_v = prolog - prolog (bpm_banded.c:222-225)
     R.bot[0] = S.B - 1 - S.prolog;
     R.base[0] = 0;
+    S.c_top_t = 0; S.c_base_t = 0; S.c_top_b = 0; S.c_bot_b = S.B - 1 - S.prolog; S.c_base_b = 0; S.c_top_b1 = 0;
+    // 32-bit bookkeeping: |fin|, k and 64 * blocks must stay below 2^30
+    if (g.k >= (1ll << 30) || g.fin >= (1ll << 30) || g.fin <= -(1ll << 30) || tk.m >= (1 << 30) || tk.n >= (1 << 30)) S.state = 2;
     int *gs = P.scores + S.scores_off;
     for (int j = 0; j < S.B; ++j) gs[j] = 64 * (j + 1);             // bpm_banded.c:180-197
     if (FULL) P.ranges[S.range_off] = make_int2(S.prolog, S.B - 1);
@@ -155,76 +163,86 @@ QB_HD void tile_slot_load(TileSlot &S, const TileRings &R, const BandTask &tk, i
 // bot = last + pos_v, pos_v = k - prolog):
 //   D1: cut_lo  -> top[k+1] in {top, top+1, top+2};   opens column block k+1 (base[k+1])
 //   D2: new bottom block (score + 64), cut_hi / clamp -> bot[k+1] in {bot, bot+1}
-// Returns true when something was decided.
-template <bool FULL>
-QB_HD bool tile_decide(TileSlot &S, const TileRings &R, const TilePools &P)
+// Tile (b, k) runs at round base[k] + b, so "tile complete" is base[k] + b < rho.  Each call takes at most ONE D1 and
+// ONE D2 in straight-line code (the lanes of the scheduler warp stay converged); one per round is all a task can need:
+// consecutive column blocks become due at least one round apart.
+QB_HD void tile_try_d1(TileSlot &S, const TileRings &R)
 {
-    bool progress = false;
-    const int RBm = R.RB - 1, RKm = R.RK - 1;
-    // D1
-    while (S.kt < S.nshift && S.kt - S.kb < R.RK - 4) {
-        const int k = S.kt;
-        const int top = R.top[k & RKm];
-        const i64 first = (i64)top - (k - S.prolog);
-        int guard;                                                  // first + 2 < last  <=>  top + 2 < bot[k]
-        if (S.kb >= k) guard = (top + 2 < R.bot[k & RKm]) ? 1 : 0;
-        else {
-            const int lo = R.bot[S.kb & RKm], hi = lo + (k - S.kb);  // bot[] never decreases and grows by <= 1 per block
-            guard = (top + 2 < lo) ? 1 : (top + 2 >= hi) ? 0 : -1;
-        }
-        if (guard < 0) break;
-        bool cut = false;
-        if (guard && S.fin > 64 * (first + 1)) {
-            if (R.base[k & RKm] + top + 1 >= S.rho) break;          // tile (top+1, k) has not completed yet
-            cut = (i64)R.sc[(k & 1) * R.RB + ((top + 1) & RBm)] + (S.fin - 64 * (first + 1)) > S.kcut;
-        }
-        int ntop = top + 1;
-        if (cut && k >= S.prolog) ++ntop;
-        else if (!cut && k < S.prolog) --ntop;
-        R.top[(k + 1) & RKm] = ntop;
-        const int b0 = R.base[k & RKm] + 1, b1 = S.rho - ntop;
-        R.base[(k + 1) & RKm] = b0 > b1 ? b0 : b1;
-        S.kt = k + 1;
-        progress = true;
+    const int RBm = R.RB - 1;
+    if (!(S.kt < S.nshift && S.kt - S.kb < R.RB - 4)) return;
+    const int k = S.kt, top = S.c_top_t;
+    const int first = top - (k - S.prolog);
+    const int lo = S.c_bot_b, hi = lo + (k - S.kb);                  // bot[] never decreases and grows by <= 1 per block
+    const int guard = (top + 2 < lo) ? 1 : (top + 2 >= hi) ? 0 : -1;   // first + 2 < last  <=>  top + 2 < bot[k]
+    if (guard < 0) return;
+    bool cut = false;
+    if (guard && S.fin > 64 * (first + 1)) {
+        if (S.c_base_t + top + 1 >= S.rho) return;                   // tile (top+1, k) has not completed yet
+        cut = R.sc[(k & 1) * R.RB + ((top + 1) & RBm)] + (S.fin - 64 * (first + 1)) > S.kcut;
     }
-    // D2
-    while (S.kb < S.nshift && S.kt >= S.kb + 1) {
-        const int k = S.kb;
-        const int top = R.top[k & RKm], bot = R.bot[k & RKm];
-        if (bot < top) { S.state = 2; return true; }                // empty band: the reference reads stale scores here
-        if (R.base[k & RKm] + bot >= S.rho) break;                  // tile (bot, k) has not completed yet
-        const i64 pos_v = k - S.prolog;
-        const i64 first1 = (i64)R.top[(k + 1) & RKm] - 1 - pos_v, last = (i64)bot - pos_v;
-        const int nbs = R.sc[(k & 1) * R.RB + (bot & RBm)] + 64;    // scores[nb] = scores[nb-1] + 64
-        R.sc[(k & 1) * R.RB + ((bot + 1) & RBm)] = nbs;
-        R.pv[(bot + 1) & RBm] = ~0ull; R.mv[(bot + 1) & RBm] = 0ull;   // the block entering at the bottom (exported if the pass ends here)
-        P.scores[S.scores_off + bot + 1] = nbs;
-        const bool cut_hi = (first1 + 2 < last) && (64 * (last - 1) > S.fin) &&
-                            ((i64)R.sc[(k & 1) * R.RB + ((bot - 1) & RBm)] + (64 * (last - 1) - S.fin) > S.kcut);
-        const int nbot = (cut_hi || bot >= S.clamp) ? bot : bot + 1;
-        R.bot[(k + 1) & RKm] = nbot;
-        S.ws += (u64)(bot - top + 1) * 64;
-        if (FULL) P.ranges[S.range_off + k + 1] = make_int2((int)(R.top[(k + 1) & RKm] - (pos_v + 1)), (int)(nbot - (pos_v + 1)));
-        S.kb = k + 1;
-        progress = true;
-    }
-    return progress;
+    int ntop = top + 1;
+    if (cut && k >= S.prolog) ++ntop;
+    else if (!cut && k < S.prolog) --ntop;
+    const int b0 = S.c_base_t + 1, b1 = S.rho - ntop;
+    const int nbase = b0 > b1 ? b0 : b1;
+    R.top[(k + 1) & RBm] = ntop;
+    R.base[(k + 1) & RBm] = nbase;
+    if (S.kb == k) S.c_top_b1 = ntop;
+    S.c_top_t = ntop; S.c_base_t = nbase;
+    S.kt = k + 1;
 }
 
-// Tiles of round S.rho; returns their count.  Finished tasks: S.state = 1.
+template <bool FULL>
+QB_HD void tile_try_d2(TileSlot &S, const TileRings &R, const TilePools &P)
+{
+    const int RBm = R.RB - 1;
+    if (!(S.kb < S.nshift && S.kt >= S.kb + 1)) return;
+    const int k = S.kb, top = S.c_top_b, bot = S.c_bot_b;
+    if (bot < top) { S.state = 2; return; }                          // empty band: the reference reads stale scores here
+    if (S.c_base_b + bot >= S.rho) return;                           // tile (bot, k) has not completed yet
+    const int pos_v = k - S.prolog;
+    const int first1 = S.c_top_b1 - 1 - pos_v, last = bot - pos_v;
+    const int nbs = R.sc[(k & 1) * R.RB + (bot & RBm)] + 64;         // scores[nb] = scores[nb-1] + 64
+    R.sc[(k & 1) * R.RB + ((bot + 1) & RBm)] = nbs;
+    R.pv[(bot + 1) & RBm] = ~0ull; R.mv[(bot + 1) & RBm] = 0ull;     // the block entering at the bottom (exported if the pass ends here)
+    P.scores[S.scores_off + bot + 1] = nbs;
+    const bool cut_hi = (first1 + 2 < last) && (64 * (last - 1) > S.fin) &&
+                        (R.sc[(k & 1) * R.RB + ((bot - 1) & RBm)] + (64 * (last - 1) - S.fin) > S.kcut);
+    const int nbot = (cut_hi || bot >= S.clamp) ? bot : bot + 1;
+    R.bot[(k + 1) & RBm] = nbot;
+    S.ws += (u64)(bot - top + 1) * 64;
+    if (FULL) P.ranges[S.range_off + k + 1] = make_int2(S.c_top_b1 - (pos_v + 1), nbot - (pos_v + 1));
+    // mirrors for kb = k + 1
+    S.c_top_b = S.c_top_b1; S.c_bot_b = nbot;
+    S.c_base_b = (S.kt == k + 1) ? S.c_base_t : R.base[(k + 1) & RBm];
+    S.c_top_b1 = (S.kt == k + 2) ? S.c_top_t : (S.kt > k + 2 ? R.top[(k + 2) & RBm] : 0);
+    S.kb = k + 1;
+}
+
+// Decisions + the tiles of round S.rho (column blocks kmin..kmax); returns their count.  Finished tasks: S.state = 1.
 template <bool FULL>
 QB_HD int tile_plan_round(TileSlot &S, const TileRings &R, const TilePools &P)
 {
-    while (tile_decide<FULL>(S, R, P)) { if (S.state) { S.cnt = 0; return 0; } }
-    const int RKm = R.RK - 1;
+    const int RBm = R.RB - 1;
+    tile_try_d1(S, R);
+    tile_try_d2<FULL>(S, R, P);
+    tile_try_d1(S, R);                                               // a new bot[kb] may have settled D1's guard
+    if (S.state) { S.cnt = 0; return 0; }
     const int kopen = (S.kt < S.K - 1) ? S.kt : S.K - 1;
-    while (S.kmax + 1 <= kopen && S.rho - R.base[(S.kmax + 1) & RKm] >= R.top[(S.kmax + 1) & RKm]) ++S.kmax;
-    while (S.kmin <= S.kmax) {
-        const int b = S.rho - R.base[S.kmin & RKm];
-        const int kk = S.kmin <= S.kb ? S.kmin : S.kb;
-        if (b <= R.bot[kk & RKm]) break;
-        if (S.kmin > S.kb) { S.state = 2; S.cnt = 0; return 0; }    // bottom of an undecided column block: cannot happen (checked by the emulator)
-        ++S.kmin;
+    if (S.kmax + 1 <= kopen) {                                       // at most one column block becomes due per round
+        const int kk = S.kmax + 1;
+        int bx, tx;
+        if (kk == S.kt) { bx = S.c_base_t; tx = S.c_top_t; } else { bx = R.base[kk & RBm]; tx = R.top[kk & RBm]; }
+        if (S.rho - bx >= tx) S.kmax = kk;
+    }
+    if (S.kmin <= S.kmax) {                                          // ... and at most one completes
+        const int km = S.kmin;
+        const int bm = (km == S.kb) ? S.c_base_b : (km == S.kt) ? S.c_base_t : R.base[km & RBm];
+        const int lim = (km >= S.kb) ? S.c_bot_b : R.bot[km & RBm];  // undecided column blocks: the last decided bottom bounds theirs
+        if (S.rho - bm > lim) {
+            if (km > S.kb) { S.state = 2; S.cnt = 0; return 0; }    // bottom of an undecided column block: cannot happen (checked by the emulator)
+            ++S.kmin;
+        }
     }
     S.cnt = S.kmax - S.kmin + 1;
     if (S.cnt <= 0) {
@@ -238,9 +256,9 @@ QB_HD int tile_plan_round(TileSlot &S, const TileRings &R, const TilePools &P)
 template <bool FULL>
 QB_HD void tile_slot_finish(TileSlot &S, const TileRings &R, const TilePools &P)
 {
-    const int RBm = R.RB - 1, RKm = R.RK - 1;
+    const int RBm = R.RB - 1;
     const int pos_v = S.nshift - S.prolog;
-    const int top = R.top[S.nshift & RKm], bot = R.bot[S.nshift & RKm];
+    const int top = R.top[S.nshift & RBm], bot = R.bot[S.nshift & RBm];
     if (S.ncols & 63) S.ws += (u64)(bot - top + 1 > 0 ? bot - top + 1 : 0) * (u64)(S.ncols & 63);
     int *gs = P.scores + S.scores_off;
     BandOut o;
@@ -257,44 +275,9 @@ QB_HD void tile_slot_finish(TileSlot &S, const TileRings &R, const TilePools &P)
             st[S.B + j] = act ? R.mv[blk & RBm] : 0ull;
         }
     }
-    (void)RKm;
 }
 
 // ---- one tile ------------------------------------------------------------------------------------------------------
-// 8 text codes (columns c0..c0+7 of the task, low byte first), each masked to the 3 code bits.
-QB_HD u64 tile_codes8(const unsigned char *text, int n, int rev, int c0)
-{
-    u64 w;
-    if (!rev) {
-        const unsigned char *p = text + c0;
-#ifdef __CUDA_ARCH__
-        const unsigned sh = (unsigned)((unsigned long long)p & 7ull) * 8u;
-        const u64 *q = reinterpret_cast<const u64 *>(p - (sh >> 3));
-        const u64 a = __ldg(q);
-        w = a >> sh;
-        if (sh) w |= __ldg(q + 1) << (64 - sh);
-#else
-        w = 0; for (int i = 0; i < 8; ++i) w |= (u64)p[i] << (8 * i);
-#endif
-    } else {
-        const unsigned char *p = text + (n - 8 - c0);               // bytes p[7]..p[0] are columns c0..c0+7
-#ifdef __CUDA_ARCH__
-        const unsigned sh = (unsigned)((unsigned long long)p & 7ull) * 8u;
-        const u64 *q = reinterpret_cast<const u64 *>(p - (sh >> 3));
-        u64 x = __ldg(q) >> sh;
-        if (sh) x |= __ldg(q + 1) << (64 - sh);
-        const u32 lo = (u32)x, hi = (u32)(x >> 32);
-        w = ((u64)__byte_perm(lo, 0, 0x0123) << 32) | (u64)__byte_perm(hi, 0, 0x0123);
-#else
-        w = 0; for (int i = 0; i < 8; ++i) w |= (u64)p[7 - i] << (8 * i);
-#endif
-    }
-    return w & 0x0707070707070707ull;
-}
-
-// One Myers block update of the tile pipeline: carry-in = top bit of wp/wm, carry-out (bit 63) shifted in at the bottom.
-// MHin enters through the adder: (((Eq|MHin) & Pv) + Pv) and ((Eq & Pv) + Pv + MHin) give the same Xh once OR-ed with
-// Eq (bit 0 by cases; above bit 0 the carries agree), so the reference's `Eq | MHin` (bpm_commons.h:51) costs nothing.
 // (a + b + (c >> 31)): on the device the top bit of c goes through the carry flag (add.cc c,c), 3 instructions in all
 QB_HD u64 add_with_top_bit(u64 a, u64 b, u32 c)
 {
@@ -335,9 +318,11 @@ QB_HD u32 byte_of(u32 w, int i)
 #endif
 }
 
-// Full tile, carry-out at bit 63.  eq: this lane's five match masks, eq[code * EQS] (EQS = 0: runtime stride eqs).
+// Full tile, carry-out at bit 63.  eq: this lane's five match masks, eq[code * EQS] (EQS = 0: runtime stride eqs);
+// tt: the tile's 64 text codes, 8 per u64 (low byte = first column), from the aligned tile-text pool; w0/w1: its first
+// two chunks, loaded by the caller long before (two chunks stay in flight: an L2 round trip outlasts 8 word-steps).
 template <int EQS>
-QB_HD void tile_fill64(u64 &pv, u64 &mv, TileCarry &c, const u64 *eq, int eqs, const unsigned char *text, int n, int rev, int col0)
+QB_HD void tile_fill64(u64 &pv, u64 &mv, TileCarry &c, const u64 *eq, int eqs, const u64 *tt, u64 w, u64 wn)
 {
     const int st = EQS ? EQS : eqs;
 #pragma unroll 1
@@ -345,8 +330,13 @@ QB_HD void tile_fill64(u64 &pv, u64 &mv, TileCarry &c, const u64 *eq, int eqs, c
         u32 wp = half ? c.p1 : c.p0, wm = half ? c.m1 : c.m0;
 #pragma unroll 1
         for (int it = 0; it < 4; ++it) {
-            const u64 w = tile_codes8(text, n, rev, col0 + half * 32 + it * 8);
             const u32 w0 = (u32)w, w1 = (u32)(w >> 32);
+            w = wn;
+#ifdef __CUDA_ARCH__
+            wn = __ldg(tt + ((half * 4 + it + 2) & 7));
+#else
+            wn = tt[(half * 4 + it + 2) & 7];
+#endif
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const u32 code = byte_of(i < 4 ? w0 : w1, i & 3);
@@ -375,60 +365,90 @@ QB_HD void tile_fill_any(u64 &pv, u64 &mv, TileCarry &c, const u64 *eq, int eqs,
     c.p0 = out_p[0]; c.p1 = out_p[1]; c.m0 = out_m[0]; c.m1 = out_m[1];
 }
 
-// Runs tile (column block k) of slot S: block b = rho - base[k].  eq: the lane's match-mask slots (stride eqs).
-template <bool FULL, int EQS>
-QB_HD void tile_run(const TileSlot &S, const TileRings &R, int k, u64 *eq, int eqs, const TilePools &P)
-{
-    const int RBm = R.RB - 1, RKm = R.RK - 1;
-    const int b = S.rho - R.base[k & RKm];
-    const int top = R.top[k & RKm];
-    const int nc = (S.ncols - 64 * k < 64) ? S.ncols - 64 * k : 64;
-    // state of the block when the tile starts
+// A tile in two halves around the CTA's mid-pass barrier.  tile_begin reads everything another tile of the same pass may
+// overwrite (the carry-outs of the block above: that block's next tile runs in this very pass) and issues the tile's
+// global loads; tile_end computes and publishes.
+struct TileIn {
+    int k, b, nc;
     u64 pv, mv;
     int sprev;
-    // first tile of this block: reset / new bottom block (with bot[k-1] still undecided the block is an old one:
-    // only blocks up to the last decided bottom run ahead of the decisions)
-    const bool fresh = (k == 0) || (k - 1 <= S.kb && b > R.bot[(k - 1) & RKm]);
-    if (fresh) {
-        pv = ~0ull; mv = 0ull;
-        sprev = (k == 0) ? 64 * (b + 1) : R.sc[((k - 1) & 1) * R.RB + (b & RBm)];
-    } else {
-        pv = R.pv[b & RBm]; mv = R.mv[b & RBm];
-        sprev = R.sc[((k - 1) & 1) * R.RB + (b & RBm)];
-    }
     TileCarry c;
-    if (b == top) { c.p0 = c.p1 = 0xffffffffu; c.m0 = c.m1 = 0u; }  // top of the band: PHin = 1, MHin = 0 (bpm_banded.c:238)
-    else c = R.carry[((S.rho - 1) & 1) * R.RB + ((b - 1) & RBm)];
+    u64 w0, w1;               // first two text chunks
+    u64 e[kAlpha];            // match masks of the block
+    bool lastblk, below;
+};
+
+template <bool FULL>
+QB_HD void tile_begin(const TileSlot &S, const TileRings &R, int k, const TilePools &P, TileIn &t)
+{
+    const int RBm = R.RB - 1;
+    const int b = S.rho - R.base[k & RBm];
+    t.k = k; t.b = b;
+    t.nc = (S.ncols - 64 * k < 64) ? S.ncols - 64 * k : 64;
+    if (b == R.top[k & RBm]) { t.c.p0 = t.c.p1 = 0xffffffffu; t.c.m0 = t.c.m1 = 0u; }  // top of the band: PHin = 1, MHin = 0 (bpm_banded.c:238)
+    else t.c = R.carry[(b - 1) & RBm];
+    {
+        const u64 *tt = P.ttext + S.tt_off + 8 * (i64)k;
+#ifdef __CUDA_ARCH__
+        t.w0 = __ldg(tt); t.w1 = __ldg(tt + 1);
+#else
+        t.w0 = tt[0]; t.w1 = tt[1];
+#endif
+        const u64 *q = P.peq + S.peq_off + (i64)b * kPeqStride;      // zero past the table: no match
+        const bool in = b < S.nbp;
+#pragma unroll
+        for (int cc = 0; cc < kAlpha; ++cc) {
+#ifdef __CUDA_ARCH__
+            t.e[cc] = in ? __ldg(q + cc) : 0ull;
+#else
+            t.e[cc] = in ? q[cc] : 0ull;
+#endif
+        }
+    }
+    // first tile of this block: reset / new bottom block (with bot[k-1] still undecided the block is an old one: only
+    // blocks up to the last decided bottom run ahead of the decisions)
+    const bool fresh = (k == 0) || (k - 1 <= S.kb && b > R.bot[(k - 1) & RBm]);
+    if (fresh) {
+        t.pv = ~0ull; t.mv = 0ull;
+        t.sprev = (k == 0) ? 64 * (b + 1) : R.sc[((k - 1) & 1) * R.RB + (b & RBm)];
+    } else {
+        t.pv = R.pv[b & RBm]; t.mv = R.mv[b & RBm];
+        t.sprev = R.sc[((k - 1) & 1) * R.RB + (b & RBm)];
+    }
+    t.lastblk = (b == S.nblk - 1) && S.mmod;                        // carry-out / score below bit 63 (level_mask)
+    const int hb = (k <= S.kb) ? R.bot[k & RBm] : R.bot[S.kb & RBm];
+    t.below = t.lastblk && (b < hb || k > S.kb);                    // a block below consumes this tile's carries
+}
+
+// eq: the lane's match-mask slots (stride EQS, or eqs when EQS = 0).
+template <bool FULL, int EQS>
+QB_HD void tile_end(const TileSlot &S, const TileRings &R, TileIn &t, u64 *eq, int eqs, const TilePools &P)
+{
+    const int RBm = R.RB - 1;
+    const int k = t.k, b = t.b;
+    u64 pv = t.pv, mv = t.mv;
+    TileCarry c = t.c;
     if (FULL) {
         TileRec *rec = P.recs + S.rec_off + (i64)k * S.B + (b - (k - S.prolog));
         rec->pv0 = pv; rec->mv0 = mv; rec->cin = c;
     }
-    // match masks of the block (zero past the table: no match)
-    {
-        const u64 *q = P.peq + S.peq_off + (i64)b * kPeqStride;
-        const bool in = b < S.nbp;
 #pragma unroll
-        for (int cc = 0; cc < kAlpha; ++cc) eq[cc * (EQS ? EQS : eqs)] = in ? q[cc] : 0ull;
-    }
-    const unsigned char *text = P.codes + S.t_off;
-    const bool lastblk = (b == S.nblk - 1) && S.mmod;               // carry-out / score below bit 63 (level_mask)
-    const int hb = (k <= S.kb) ? R.bot[k & RKm] : R.bot[S.kb & RKm];
-    const bool below = lastblk && (b < hb || k > S.kb);             // a block below consumes this tile's carries
+    for (int cc = 0; cc < kAlpha; ++cc) eq[cc * (EQS ? EQS : eqs)] = t.e[cc];
     int delta;
-    if (nc == 64 && !below) {
-        const int adj0 = lastblk ? popc64(pv >> S.mmod) - popc64(mv >> S.mmod) : 0;
-        tile_fill64<EQS>(pv, mv, c, eq, eqs, text, S.n, S.rev, 64 * k);
+    if (t.nc == 64 && !t.below) {
+        const int adj0 = t.lastblk ? popc64(pv >> S.mmod) - popc64(mv >> S.mmod) : 0;
+        tile_fill64<EQS>(pv, mv, c, eq, eqs, P.ttext + S.tt_off + 8 * (i64)k, t.w0, t.w1);
         delta = popc32(c.p0) + popc32(c.p1) - popc32(c.m0) - popc32(c.m1);
         // score of the last pattern block follows row m-1, not row 63 of the block: D[m-1] = D[63] - sum of the vertical
         // deltas of the padding rows, which the block's own Pv/Mv hold
-        if (lastblk) delta += adj0 - (popc64(pv >> S.mmod) - popc64(mv >> S.mmod));
+        if (t.lastblk) delta += adj0 - (popc64(pv >> S.mmod) - popc64(mv >> S.mmod));
     } else {
-        tile_fill_any(pv, mv, c, eq, EQS ? EQS : eqs, text, S.n, S.rev, 64 * k, nc, lastblk ? S.mmod - 1 : 63);
+        tile_fill_any(pv, mv, c, eq, EQS ? EQS : eqs, P.codes + S.t_off, S.n, S.rev, 64 * k, t.nc, t.lastblk ? S.mmod - 1 : 63);
         delta = popc32(c.p0) + popc32(c.p1) - popc32(c.m0) - popc32(c.m1);
     }
     R.pv[b & RBm] = pv; R.mv[b & RBm] = mv;
-    R.carry[(S.rho & 1) * R.RB + (b & RBm)] = c;
-    const int sc = sprev + delta;
+    R.carry[b & RBm] = c;
+    const int sc = t.sprev + delta;
     R.sc[(k & 1) * R.RB + (b & RBm)] = sc;
     P.scores[S.scores_off + b] = sc;
 }
@@ -439,11 +459,12 @@ QB_HD void tile_run(const TileSlot &S, const TileRings &R, int k, u64 *eq, int e
 namespace qb {
 
 // ---- the kernel ----------------------------------------------------------------------------------------------------
-// One persistent CTA = `lanes` compute threads + one scheduler warp (the last).  Per pass:
-//   scheduler warp: lane s owns task slot s — advances the band decisions, plans the slot's next round, loads a new task
-//                   into a free slot; then the warp packs the ready tiles of all slots onto the compute lanes
-//                   (work-conserving: a slot's round may be split over passes)            -> __syncthreads
-//   compute warps : one tile (64 word-steps) per lane                                      -> __syncthreads
+// One persistent CTA = LANES compute threads + one scheduler warp (the last).  Per pass:
+//   scheduler warp: lane s owns task slot s (its bookkeeping in registers) — band decisions, the slot's next round, a new
+//                   task into a free slot; then the warp packs the ready tiles of all slots onto the compute lanes
+//                   (work-conserving: a round may be split over passes)                       -> __syncthreads
+//   compute warps : tile_begin (inputs another tile of the pass may overwrite, global loads)  -> __syncthreads
+//                   tile_end (64 word-steps per lane, results)                                -> __syncthreads
 struct TileLaunch {
     const int *list;      // task ids handled by this launch (one band-height class)
     const int *count;     // how many (device memory: the list is built on the device)
@@ -452,21 +473,19 @@ struct TileLaunch {
     int RB, nslots, lanes;
 };
 
-constexpr int kTileLanesMax = 256;
-
 __host__ __device__ inline size_t tile_smem_bytes(int RB, int nslots, int lanes)
 {
-    size_t b = 16 + (size_t)lanes * 4;
+    size_t b = 16 + (size_t)lanes * 4;                       // control words + the plan
     b = (b + 15) & ~(size_t)15;
     b += (size_t)nslots * sizeof(TileSlot);
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)kAlpha * lanes * 8;
+    b += (size_t)kAlpha * lanes * 8;                        // match masks per lane
     b += (size_t)nslots * tile_slot_arena_bytes(RB);
     return b;
 }
 
 template <bool FULL, int LANES>
-__global__ void __launch_bounds__(LANES + 32) k_band_tiles(TilePools P, TileLaunch Q)
+__global__ void __launch_bounds__(LANES + 32, LANES >= 128 ? 4 : LANES >= 64 ? 6 : 8) k_band_tiles(TilePools P, TileLaunch Q)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     constexpr int lanes = LANES;
@@ -489,13 +508,16 @@ __global__ void __launch_bounds__(LANES + 32) k_band_tiles(TilePools P, TileLaun
     const int n_tasks = sched ? *Q.count : 0;
     bool exhausted = false;
     const bool mine = sched && lane < nslots;
-    TileRings R = tile_rings(arenas + (size_t)(mine ? lane : 0) * ab, RB);
+    const TileRings R = tile_rings(arenas + (size_t)(mine ? lane : 0) * ab, RB);
+    TileSlot S;                                            // scheduler lanes: the slot, in registers
+    S.task = -1; S.cnt = 0; S.koff = 0; S.rho = 0; S.kb = 0; S.state = 0;
+    long long t_sched = 0, t_all0 = clock64(), n_pass = 0;
 
     for (unsigned pass = 0;; ++pass) {
         if (sched) {
+            const long long t_s0 = clock64();
             int want = 0, kstart = 0;
             if (mine) {
-                TileSlot &S = slots[lane];
                 bool need_plan = false;
                 if (S.task >= 0 && S.koff >= S.cnt) { ++S.rho; need_plan = true; }
                 for (;;) {
@@ -505,10 +527,11 @@ __global__ void __launch_bounds__(LANES + 32) k_band_tiles(TilePools P, TileLaun
                         if (idx >= n_tasks) { exhausted = true; break; }
                         const int ti = Q.list[idx];
                         tile_slot_load<FULL>(S, R, P.tasks[ti], ti, P);
+                        slots[lane] = S;
                         need_plan = true;
                     }
                     if (!need_plan) break;
-                    tile_plan_round<FULL>(S, R, P);
+                    if (!S.state) tile_plan_round<FULL>(S, R, P);
                     S.koff = 0;
                     if (S.state == 1) {
                         tile_slot_finish<FULL>(S, R, P);
@@ -526,56 +549,99 @@ __global__ void __launch_bounds__(LANES + 32) k_band_tiles(TilePools P, TileLaun
                     if (S.cnt == 0) { ++S.rho; continue; }              // no tile is due in this round
                     break;
                 }
-                if (S.task >= 0) { want = S.cnt - S.koff; kstart = S.kmin + S.koff; }
+                if (S.task >= 0) {
+                    want = S.cnt - S.koff; kstart = S.kmin + S.koff;
+                    slots[lane].rho = S.rho; slots[lane].kb = S.kb;
+                }
             }
             // pack: exclusive scan of `want` in an order that rotates every pass (no slot waits forever)
             const int rot = (int)(pass & 31u);
-            int x = __shfl_sync(kFull, want, (lane + rot) & 31);       // x of lane v = want of slot (v + rot) & 31
+            const int x = __shfl_sync(kFull, want, (lane + rot) & 31);       // x of lane v = want of slot (v + rot) & 31
             int incl = x;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += y; }
-            const int excl_v = incl - x;
-            const int excl = __shfl_sync(kFull, excl_v, (lane - rot) & 31);   // back to slot order
+            const int excl = __shfl_sync(kFull, incl - x, (lane - rot) & 31);  // back to slot order
             int take = lanes - excl;
             take = take < 0 ? 0 : (take > want ? want : take);
-            if (mine && take > 0) {
-                slots[lane].koff += take;
+            if (take > 0) {
+                S.koff += take;
                 for (int i = 0; i < take; ++i) plan[excl + i] = ((u32)lane << 24) | (u32)(kstart + i);
             }
             const int total = __shfl_sync(kFull, incl, 31);
             for (int i = (total < lanes ? total : lanes) + lane; i < lanes; i += 32) plan[i] = 0xffffffffu;
-            const bool idle = !mine || (slots[lane].task < 0 && exhausted);
+            const bool idle = !mine || (S.task < 0 && exhausted);
             if (__all_sync(kFull, idle) && lane == 0) ctl[0] = 1;
+            t_sched += clock64() - t_s0; ++n_pass;
         }
         __syncthreads();
         if (ctl[0]) break;
+        TileIn t;
+        int s = -1;
         if (!sched) {
             const u32 e = plan[tid];
             if (e != 0xffffffffu) {
-                const int s = (int)(e >> 24), k = (int)(e & 0xffffffu);
-                const TileRings Rs = tile_rings(arenas + (size_t)s * ab, RB);
-                tile_run<FULL, LANES>(slots[s], Rs, k, s_eq + tid, lanes, P);
+                s = (int)(e >> 24);
+                tile_begin<FULL>(slots[s], tile_rings(arenas + (size_t)s * ab, RB), (int)(e & 0xffffffu), P, t);
             }
         }
         __syncthreads();
+        if (s >= 0) tile_end<FULL, LANES>(slots[s], tile_rings(arenas + (size_t)s * ab, RB), t, s_eq + tid, lanes, P);
+        __syncthreads();
+    }
+    if (tid == lanes) {                                   // scheduler lane 0: cycles spent scheduling / in all / passes
+        atomicAdd(&Q.counters[8], (u64)t_sched);
+        atomicAdd(&Q.counters[9], (u64)(clock64() - t_all0));
+        atomicAdd(&Q.counters[10], (u64)n_pass);
     }
 }
 
-// Task ids of `list` sorted into band-height classes (ring size 8 << c): out[c * cap + i], counts[c].
+// Task ids of `list` sorted into band-height classes (ring size 8 << c): out[c * cap + i], counts[c]; every task also
+// gets its place in the tile-text pool (tt_words: running total in u64 words).
 template <bool FULL>
-__global__ void __launch_bounds__(256) k_tile_classes(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n,
-                                                      int *__restrict__ out, int cap, int *__restrict__ counts)
+__global__ void __launch_bounds__(256) k_tile_classes(BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n,
+                                                      int *__restrict__ out, int cap, int *__restrict__ counts,
+                                                      unsigned long long *__restrict__ tt_words)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int ti = list ? list[begin + i] : begin + i;
-    const BandTask &t = tasks[ti];
+    BandTask &t = tasks[ti];
     const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
     const int rb = tile_ring_for(FULL ? g.Bc : g.Bs);
     if (rb > kTileMaxRing) return;                       // taller bands: the shared-memory sweep kernel (qb_banded.cuh)
     int c = 0;
     while ((8 << c) < rb) ++c;
     out[(size_t)c * cap + atomicAdd(&counts[c], 1)] = ti;
+    const int ncols = FULL ? t.n : t.finish;
+    t.tt_off = (i64)atomicAdd(tt_words, (unsigned long long)((ncols + 63) / 64 * 8 + 1));   // +1: the prefetch past the last tile
+}
+
+// Tile-text pool: the text codes of a task, masked to the 3 code bits, in COLUMN order (a reversed pass reads its text
+// backwards), 8 columns per u64 and 8-byte aligned, so a tile's 64 codes are eight aligned loads with no realignment
+// in the fill's inner loop.  One warp per task; columns past the pass (ncols..64*ceil) are code 4.
+template <bool FULL>
+__global__ void __launch_bounds__(256) k_tile_text(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n,
+                                                   const unsigned char *__restrict__ codes, u64 *__restrict__ ttext)
+{
+    const int wi = (int)(((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (wi >= n) return;
+    const BandTask &t = tasks[list ? list[begin + wi] : begin + wi];
+    const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
+    if (tile_ring_for(FULL ? g.Bc : g.Bs) > kTileMaxRing) return;
+    const int ncols = FULL ? t.n : t.finish;
+    const int nw = (ncols + 63) / 64 * 8;
+    const unsigned char *src = codes + t.t_off;
+    u64 *dst = ttext + t.tt_off;
+    for (int w = lane; w <= nw; w += 32) {
+        u64 v = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int col = 8 * w + b;
+            const unsigned cd = col < ncols ? (unsigned)(src[t.rev ? t.n - 1 - col : col] & 7u) : 4u;
+            v |= (u64)cd << (8 * b);
+        }
+        dst[w] = v;
+    }
 }
 
 }  // namespace qb

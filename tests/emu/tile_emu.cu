@@ -88,15 +88,28 @@ static void build_peq(std::vector<u64> &peq, i64 off, const unsigned char *codes
 template <bool FULL>
 static u64 emulate(Emu &E, int RB, int nslots, int L, bool shuffle)
 {
+    // tile-text pool (device: k_tile_classes + k_tile_text)
+    std::vector<u64> ttext;
+    for (auto &t : E.tasks) {
+        const int ncols = FULL ? t.n : t.finish;
+        const int nw = (ncols + 63) / 64 * 8;
+        t.tt_off = (i64)ttext.size();
+        for (int w = 0; w <= nw; ++w) {
+            u64 v = 0;
+            for (int b = 0; b < 8; ++b) { const int col = 8 * w + b; const unsigned cd = col < ncols ? (E.codes[t.t_off + (t.rev ? t.n - 1 - col : col)] & 7u) : 4u; v |= (u64)cd << (8 * b); }
+            ttext.push_back(v);
+        }
+    }
     TilePools P;
+    P.ttext = ttext.data();
     P.tasks = E.tasks.data(); P.codes = E.codes.data(); P.peq = E.peq.data(); P.recs = E.recs.data();
     P.ranges = E.ranges.data(); P.scores = E.scores.data(); P.state = E.state.data(); P.outs = E.outs.data();
     P.punt_list = E.punt.data(); P.punt_count = &E.punt_count; P.rec_sub = 0;
     std::vector<TileSlot> slots(nslots);
     std::vector<std::vector<unsigned char>> arena(nslots, std::vector<unsigned char>(tile_slot_arena_bytes(RB)));
     std::vector<TileRings> rings(nslots);
-    for (int s = 0; s < nslots; ++s) { slots[s].task = -1; rings[s] = tile_rings(arena[s].data(), RB); }
-    std::vector<char> ran(nslots, 0);
+    for (int s = 0; s < nslots; ++s) { slots[s].task = -1; slots[s].cnt = 0; slots[s].koff = 0; rings[s] = tile_rings(arena[s].data(), RB); }
+    std::vector<char> need_plan(nslots, 0);
     std::vector<u64> eq((size_t)kAlpha * L);
     size_t next = 0;
     u64 ws = 0, rounds = 0, lane_rounds = 0, busy = 0;
@@ -108,8 +121,8 @@ static u64 emulate(Emu &E, int RB, int nslots, int L, bool shuffle)
         for (int v = 0; v < nslots; ++v) {
             const int s = (v + rot) % nslots;
             TileSlot &S = slots[s];
-            if (S.task >= 0 && ran[s]) ++S.rho;
-            ran[s] = 0;
+            if (S.task >= 0 && S.koff >= S.cnt) { ++S.rho; need_plan[s] = 1; }
+            int spin = 0;
             for (;;) {
                 if (S.task < 0) {
                     while (next < E.tasks.size()) {
@@ -118,30 +131,46 @@ static u64 emulate(Emu &E, int RB, int nslots, int L, bool shuffle)
                         const int B = (int)(FULL ? g.Bc : g.Bs);
                         if (tile_ring_for(B) > RB) { fprintf(stderr, "task %zu needs ring %d > %d\n", next, tile_ring_for(B), RB); exit(2); }
                         tile_slot_load<FULL>(S, rings[s], tk, (int)next, P);
+                        need_plan[s] = 1;
                         ++next;
                         break;
                     }
                     if (S.task < 0) break;
                 }
-                const int cnt = tile_plan_round<FULL>(S, rings[s], P);
-                if (S.state == 1) { tile_slot_finish<FULL>(S, rings[s], P); ws += S.ws; S.task = -1; continue; }
-                if (S.state == 2) { E.punt[E.punt_count++] = S.task; S.task = -1; continue; }
+                if (need_plan[s]) {
+                    if (!S.state) tile_plan_round<FULL>(S, rings[s], P);
+                    S.koff = 0;
+                    if (S.state == 1) { tile_slot_finish<FULL>(S, rings[s], P); ws += S.ws; S.task = -1; continue; }
+                    if (S.state == 2) { E.punt[E.punt_count++] = S.task; S.task = -1; continue; }
+                    if (S.cnt == 0) { ++S.rho; if (++spin > 100000) { fprintf(stderr, "slot spins without a due tile\n"); exit(3); } continue; }
+                    need_plan[s] = 0;
+                }
                 any = true;
-                if (cnt > 0 && (int)plan.size() + cnt <= L) {
-                    for (int i = 0; i < cnt; ++i) plan.push_back(((unsigned)s << 24) | (unsigned)(S.kmin + i));
-                    ran[s] = 1;
-                } else if (cnt > L) { fprintf(stderr, "slot needs %d lanes > %d\n", cnt, L); exit(2); }
+                {
+                    const int want = S.cnt - S.koff, room = L - (int)plan.size();
+                    const int take = want < room ? want : room;
+                    for (int i = 0; i < take; ++i) plan.push_back(((unsigned)s << 24) | (unsigned)(S.kmin + S.koff + i));
+                    S.koff += take;
+                }
                 break;
             }
         }
         if (!any) break;
         if (plan.empty()) { fprintf(stderr, "deadlock: no tile ready\n"); exit(3); }
-        // ---- compute phase ----
+        // ---- compute phase: every lane's tile_begin, the mid-pass barrier, every lane's tile_end ----
         if (shuffle) for (size_t i = plan.size(); i > 1; --i) std::swap(plan[i - 1], plan[rnd() % i]);
+        std::vector<TileIn> tin(plan.size());
         for (size_t g = 0; g < plan.size(); ++g) {
             const int s = (int)(plan[g] >> 24), k = (int)(plan[g] & 0xffffffu);
-            tile_run<FULL, 0>(slots[s], rings[s], k, eq.data() + g, L, P);
+            tile_begin<FULL>(slots[s], rings[s], k, P, tin[g]);
         }
+        if (shuffle) {      // tile_end in another order than tile_begin
+            std::vector<size_t> ord(plan.size());
+            for (size_t i = 0; i < ord.size(); ++i) ord[i] = i;
+            for (size_t i = ord.size(); i > 1; --i) std::swap(ord[i - 1], ord[rnd() % i]);
+            for (size_t g : ord) tile_end<FULL, 0>(slots[(int)(plan[g] >> 24)], rings[(int)(plan[g] >> 24)], tin[g], eq.data() + g, L, P);
+        } else
+            for (size_t g = 0; g < plan.size(); ++g) tile_end<FULL, 0>(slots[(int)(plan[g] >> 24)], rings[(int)(plan[g] >> 24)], tin[g], eq.data() + g, L, P);
         ++rounds; lane_rounds += L; busy += plan.size();
     }
     fprintf(stderr, "  [emu] %zu tasks, RB %d, %d slots, %d lanes: %llu rounds, lane utilisation %.3f, %d punts\n", E.tasks.size(), RB, nslots, L,

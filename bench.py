@@ -5,13 +5,19 @@
   python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation on the host cores
 
 A "step" is one pass of the hot path (QUICKED: WindowEd bound -> BandEd/Hirschberg alignment -> score + CIGAR)
-over one batch of synthetic pairs.  The default workload is BASELINE.json configs[1]: 1 kbp pairs at 10 % error,
-1 M pairs per GPU (weak scaling: every rank aligns its own contiguous index range; there is no collective on the
-data path, only the barrier + max-over-ranks of the timing).
+over one batch of synthetic pairs.  The default workload is the configuration BASELINE.json's target is quoted on:
+configs[2], 100 k pairs of 10 kbp at 20 % error, QUICKED score + CIGAR (--algo banded / windowed give the two other
+algorithms configs[2] names).  With N GPUs the SAME job is cut into contiguous index ranges, one per rank (strong
+scaling; every pair has its own random stream, so a rank generates exactly its slice); there is no collective on the
+data path, only the barrier + max-over-ranks of the timing.
 
-  value : alignments/s, whole job, inputs already resident in HBM when the timed region starts (kernel path only)
-  e2e   : the same metric through qb200_align_batch() with HOST buffers — pinned-host ASCII in, host scores +
-          CIGAR text out, both copies inside the timed region
+  value    : alignments/s, whole job, inputs already resident in HBM when the timed region starts (kernel path only)
+  e2e      : the same metric through qb200_align_batch() with HOST buffers — pinned-host ASCII in, host scores +
+             CIGAR text out, both copies inside the timed region
+  roofline : integer-ALU roofline of the dominant kernel (24 int32 ops per word-step) against the measured
+             LOP3+IADD3 peak; int_alu_roofline is the same arithmetic for the whole step
+  parity   : the CPU baseline leg aligns a sample of the very pairs the GPU timed; every sampled score must equal the
+             reference's and a strided subset of the GPU's CIGARs is replayed against the sequences
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -28,7 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {   # name: (length, error, pairs per GPU, description)
+WORKLOADS = {   # name: (length, error, pairs of the job, description)
     "c1": (100, 0.05, 100000, "generate_dataset 100 bp pairs at 5% error, 100k pairs"),
     "c2": (1000, 0.10, 1000000, "generate_dataset 1 kbp pairs at 10% error, 1M pairs, QuickEd score + CIGAR"),
     "c3": (10000, 0.20, 100000, "generate_dataset 10 kbp pairs at 20% error, 100k pairs, score + CIGAR"),
@@ -54,22 +60,65 @@ def generate_c5(base_pairs, seed):
 ALGOS = {"quicked": 0, "windowed": 1, "banded": 2, "hirschberg": 3}
 
 
-def ncu_traffic_bytes(kernel_substr, csv_name="r1_ncu_full_c2_v7_raw.csv"):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel_substr`, from the committed `ncu --set full`
-    capture of this same command (profiles/, 1 M pairs of configs[1]); None when the capture is not there."""
+def ncu_traffic(args):
+    """{kernel name: dram__bytes_read.sum + dram__bytes_write.sum per launch} from the committed `ncu --set full` capture of
+    this same command (profiles/r2_ncu_<workload>_<algo>_raw.csv); {} when the capture is not there."""
     import csv
-    path = os.path.join(ROOT, "profiles", csv_name)
+    path = os.path.join(ROOT, "profiles", f"r2_ncu_{args.workload}_{args.algo}_raw.csv")
+    out = {}
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
         ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         for r in rows[2:]:
-            if kernel_substr in r[ik]:
-                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+            name = r[ik].split("(")[0].split("<")[0].replace("void ", "").strip()
+            out[name] = out.get(name, 0.0) + float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
     except Exception:
-        return None
-    return None
+        return {}
+    return out
+
+
+def replay_cigar(cigar, pattern, text):
+    """Replay a run-length CIGAR (M match, X mismatch, I consumes a text character, D a pattern character: reference
+    cigar.c:363-434) against the two sequences.  -> its edit cost, or -1 if it does not reproduce the sequences."""
+    import re
+    v = h = cost = 0
+    for num, op in re.findall(rb"(\d+)([MXID])", cigar):
+        k = int(num)
+        if op in b"MX":
+            a, b = pattern[v:v + k], text[h:h + k]
+            if len(a) != k or len(b) != k:
+                return -1
+            if op == b"M" and a != b:
+                return -1
+            if op == b"X" and any(x == y for x, y in zip(a, b)):
+                return -1
+            v += k; h += k
+        elif op == b"I":
+            h += k
+        else:
+            v += k
+        if op != b"M":
+            cost += k
+    return cost if (v == len(pattern) and h == len(text)) else -1
+
+
+def gather_pairs(seqs, po, pl, to, tl, sel):
+    """the pairs `sel` of a packed batch, re-packed back to back (pattern NUL text NUL) -> (seqs, po, pl, to, tl)"""
+    pl2, tl2 = np.ascontiguousarray(pl[sel]), np.ascontiguousarray(tl[sel])
+    sizes = pl2.astype(np.int64) + tl2 + 2
+    base = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    po2 = base
+    to2 = base + pl2 + 1
+    total = int(sizes.sum())
+    out = np.zeros((total + 15) // 16 * 16 + 16, np.uint8)
+    for src, ln, dst in ((po[sel], pl2, po2), (to[sel], tl2, to2)):
+        ln64 = ln.astype(np.int64)
+        idx = np.repeat(src - np.concatenate([[0], np.cumsum(ln64)[:-1]]), ln64) + np.arange(int(ln64.sum()))
+        jdx = np.repeat(dst - np.concatenate([[0], np.cumsum(ln64)[:-1]]), ln64) + np.arange(int(ln64.sum()))
+        out[jdx] = seqs[idx]
+    return out, np.ascontiguousarray(po2), pl2, np.ascontiguousarray(to2), tl2
 
 
 def bind_to_gpu_numa_node(torch, local_rank):
@@ -153,8 +202,7 @@ def cpu_reference_arm(length, error, algo_kw, sample_pairs, seed, threads=None):
     call (oracle/_ref/libref_batch.so = the unmodified reference driven like its own align_benchmark does per thread;
     else the oracle port), so no Python overhead lands in the timed region.  -> (pairs/s, threads, kind, seconds)"""
     from oracle import harness
-    import quicked_b200 as qb
-    seqs, po, pl, to, tl = qb.generate_pairs_native(seed, sample_pairs, length, error)
+    seqs, po, pl, to, tl = harness.generate_pairs(seed, sample_pairs, length, error)     # oracle/datagen.c: no product code in this arm
     threads = max(1, min(threads or os.cpu_count() or 1, sample_pairs))
     harness.cpu_batch_align(seqs, po[:threads], pl[:threads], to[:threads], tl[:threads], threads, **algo_kw)   # warm the libraries
     t0 = time.perf_counter()
@@ -169,9 +217,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: split ONE job (strong) or one job per GPU (weak)")
     ap.add_argument("--algo", default="quicked", choices=sorted(ALGOS))
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs of the job (weak scaling: per GPU); default: the workload's")
     ap.add_argument("--bandwidth", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,7 +259,7 @@ def main():
         v = sum(sample for _ in vals) / sum(dt for _, dt in vals)
         ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
         out = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "u64", "data": "synthetic", "config": config,
                "cpu_baseline": {"value": v, "unit": unit, "cores": used, "kind": kind,
                                 "sample": f"{sample} pairs of the workload per step, {used} host threads"},
@@ -223,6 +272,7 @@ def main():
     import torch
     import torch.distributed as dist
     import quicked_b200 as qb
+    from quicked_b200.sharding import shard_range, strided_deal
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the QuickEd GPU path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -244,24 +294,38 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    scaling = "weak"
+    def all_ranks(x):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    scaling = args.scaling if world > 1 else "strong"
+    job_pairs = n_pairs
     if args.workload == "c5":
-        # strong scaling: ONE mixed job, length-bucketed, cut into contiguous work-balanced ranges (no collective)
-        from quicked_b200.sharding import balanced_ranges
-        seqs, po, pl, to, tl = generate_c5(n_pairs, 77)
-        lo, hi = balanced_ranges(list(zip(pl.tolist(), tl.tolist())), world)[rank]
-        b0 = int(min(po[lo], to[lo])) & ~15
-        b1 = int(max(po[hi - 1] + pl[hi - 1], to[hi - 1] + tl[hi - 1]))
-        seqs = np.ascontiguousarray(np.concatenate([seqs[b0:b1], np.zeros((-(b1 - b0)) % 16 + 16, np.uint8)]))
-        po, to, pl, tl = po[lo:hi] - b0, to[lo:hi] - b0, np.ascontiguousarray(pl[lo:hi]), np.ascontiguousarray(tl[lo:hi])
-        config["job_pairs"] = int(sum(max(1, n_pairs * 100 // L // len(C5_ERRORS)) * len(C5_ERRORS) for L in C5_LENGTHS))
-        config["rank0_pairs"] = int(hi - lo)
-        length = int(np.sqrt(float(np.mean(pl.astype(np.float64) * tl))))     # for the GCUPS_equiv line only
-        n_pairs = int(hi - lo)
+        # strong scaling of ONE mixed job: pairs sorted by estimated work and dealt round-robin to the ranks, so every GPU
+        # gets the same mix of lengths and error rates (no collective; results go back by index)
         scaling = "strong"
+        seqs, po, pl, to, tl = generate_c5(n_pairs, 77)
+        job_pairs = int(po.size)
+        sel = strided_deal(pl, tl, rank, world)
+        seqs, po, pl, to, tl = gather_pairs(seqs, po, pl, to, tl, sel)
+        config["job_pairs"] = job_pairs
+        config["rank0_pairs"] = int(sel.size)
+        config["sharding"] = f"work-sorted round-robin deal x{world}, results gathered by index, no collective"
+        length = int(np.sqrt(float(np.mean(pl.astype(np.float64) * tl))))     # for the GCUPS_equiv line only
+        n_pairs = int(sel.size)
+    elif scaling == "strong":
+        lo, hi = shard_range(job_pairs, rank, world)      # rank r aligns pairs [lo, hi) of the one job (seed 1000)
+        n_pairs = hi - lo
+        seqs, po, pl, to, tl = qb.generate_pairs_native(1000, n_pairs, length, error, first=lo)
+        config["pairs_per_gpu"] = n_pairs
+        config["job_pairs"] = job_pairs
     else:
-        # rank r aligns the contiguous index range [r*n_pairs, (r+1)*n_pairs) of the (virtual) job
-        seqs, po, pl, to, tl = qb.generate_pairs_native(1000 + rank, n_pairs, length, error)
+        seqs, po, pl, to, tl = qb.generate_pairs_native(1000 + rank, n_pairs, length, error)   # one job per GPU
+        job_pairs = world * n_pairs
     lib = qb.load()
     # pinned host staging for the end-to-end leg
     import ctypes as C
@@ -277,7 +341,6 @@ def main():
     gpu.upload_arrays(pinned, po, pl, to, tl)
     for _ in range(args.warmup):
         gpu.run(params)
-    # one sampler per rank on its own GPU; QB_NO_SMI=1 disables it (nvidia-smi polling can perturb short steps)
     # one nvidia-smi poller is enough (rank 0 prints the line); eight of them only compete with the ranks for the driver
     sampler = ClockSampler(None if (os.environ.get("QB_NO_SMI") or rank != 0) else local_rank)
     barrier()
@@ -296,19 +359,14 @@ def main():
     ev1.record()
     barrier()
     clocks = sampler.stop()
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    ms_step = ms_total / args.steps
-    total_pairs = world * n_pairs
-    if scaling == "strong" and world > 1:
-        tp = torch.tensor([float(n_pairs)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tp)
-        total_pairs = int(tp.item())
-    elif scaling == "strong":
-        total_pairs = n_pairs
-    value = total_pairs / (ms_step * 1e-3)
+    my_ms = ev0.elapsed_time(ev1) / args.steps
+    rank_ms = all_ranks(my_ms)
+    ms_step = max(rank_ms)
+    value = job_pairs / (ms_step * 1e-3)
     st = gpu.stats()
     status, score, off, cig = gpu.download()
     ok_frac = float((status >= 0).mean())
+    ws_all = all_ranks(float(st["word_steps"]))
 
     # ---- end to end through the C-ABI with host buffers (H2D + kernels + D2H inside the timed region) ----
     score_h = np.empty(n_pairs, np.int32); status_h = np.empty(n_pairs, np.int32); off_h = np.zeros(n_pairs + 1, np.int64)
@@ -331,70 +389,93 @@ def main():
     torch.cuda.synchronize()
     dt = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = total_pairs * args.steps / dt
+    e2e_value = job_pairs * args.steps / dt
     st_e = gpu.stats()
     assert np.array_equal(score_h, score), "end-to-end scores differ from the resident run"
+    h2d_all, d2h_all = sum(all_ranks(float(st_e["h2d_bytes"]))), sum(all_ranks(float(st_e["d2h_bytes"])))
 
-    # ---- roofline of the dominant kernel ----
+    # ---- rooflines (the path is 64-bit bitwise work, bounded by the integer ALU issue rate) ----
     peaks, peak_kind = measured_peaks()
     stage_avg = {k: v / args.steps for k, v in stage.items() if k != "ms_total"}
     dom = max(stage_avg, key=stage_avg.get) if stage_avg else None
     int_peak = gpu.int_peak_tops()
-    # the traceback-state fill: every word-step writes its 16-byte (Pv,Mv) entry (SURVEY §8d "spilled-matrix": 16 B/word-step)
-    fill_ms = stage_avg.get("ms_align_fill", 0.0)
-    fill_bytes = 16.0 * st["word_steps_banded"]
-    roof = None
-    if fill_ms > 0:
-        ach = fill_bytes / (fill_ms * 1e-3) / 1e9
-        roof = {"kernel": "k_banded_thread/k_banded_warp (BandEd full-matrix fill)", "bound": "hbm", "achieved": ach,
-                "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": ach / peaks.get("hbm_gbs"),
-                "traffic": ncu_traffic_bytes("k_banded_thread") if (args.workload == "c2" and n_pairs == 1000000 and args.algo == "quicked") else None,
-                "algorithmic_bytes": fill_bytes,
-                "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs", "algorithmic_bytes_per_word_step": 16,
-                "ms_per_launch": fill_ms}
-    int_roof = {"achieved_tops": 24.0 * st["word_steps"] / (ms_step * 1e-3) / 1e12, "peak_tops": int_peak,
-                "frac": 24.0 * st["word_steps"] / (ms_step * 1e-3) / 1e12 / int_peak if int_peak else None,
-                "ops_per_word_step": 24, "word_steps_per_step": st["word_steps"],
+    traffic = ncu_traffic(args) if (world == 1 and n_pairs == WORKLOADS[args.workload][2]) else {}
+    kern = []      # (kernel, CUDA-event ms per step, word-steps per step)
+    if stage_avg.get("ms_align_fill", 0) > 0:
+        kern.append(("k_band_tiles (BandEd fill)" if st["word_steps_banded"] else "fill", "k_band_tiles", stage_avg["ms_align_fill"], st["word_steps_banded"]))
+    if stage_avg.get("ms_windowed_s", 0) > 0:
+        kern.append(("k_windowed21_score (WindowEd(S) bound)", "k_windowed21_score", stage_avg["ms_windowed_s"], st["word_steps_windowed"]))
+    if stage_avg.get("ms_windowed_l", 0) > 0 and args.algo == "windowed":
+        kern.append(("k_windowed_warp (WindowEd)", "k_windowed_warp", stage_avg["ms_windowed_l"], st["word_steps_windowed"]))
+    if stage_avg.get("ms_fused", 0) > 0:
+        kern.append(("k_quicked_fused (WindowEd(S) + fill + traceback)", "k_quicked_fused", stage_avg["ms_fused"], st["word_steps"]))
+    roofs = []
+    for name, key, ms, ws in kern:
+        a = 24.0 * ws / (ms * 1e-3) / 1e12
+        roofs.append({"kernel": name, "bound": "int_alu", "achieved": a, "peak": int_peak, "unit": "T int32-op/s",
+                      "frac": a / int_peak if int_peak else None, "traffic": traffic.get(key), "ops_per_word_step": 24,
+                      "word_steps_per_launch": int(ws), "ms_per_launch": ms,
+                      "peak_source": "qb200_measure_int_peak (LOP3+IADD3 microbenchmark, this run); MEASURED_PEAKS.json has no integer peak"})
+    roofs.sort(key=lambda r: -r["ms_per_launch"])
+    roof = roofs[0] if roofs else None
+    ws_total = sum(ws_all)
+    int_roof = {"achieved_tops": 24.0 * ws_total / (ms_step * 1e-3) / 1e12, "peak_tops": int_peak * world,
+                "frac": 24.0 * ws_total / (ms_step * 1e-3) / 1e12 / (int_peak * world) if int_peak else None,
+                "ops_per_word_step": 24, "word_steps_per_step": int(ws_total),
                 "peak_source": "qb200_measure_int_peak (LOP3+IADD3 microbenchmark, this run)"}
+    # secondary: HBM.  Algorithmic bytes of a step = the characters in + scores and CIGAR text out; the traceback state is
+    # tile records (32 B per 64 word-steps), recomputed on chip by the walk
+    alg_bytes = float(pinned.size) + float(cig.size if cig is not None else 0) + 8.0 * n_pairs
+    hbm_roof = {"bound": "hbm", "achieved": alg_bytes / (my_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": alg_bytes / (my_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs"), "algorithmic_bytes": alg_bytes,
+                "traffic": sum(traffic.values()) if traffic else None, "traffic_by_kernel": traffic or None,
+                "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs"}
 
-    # the other two big kernels, for the record (not the `roofline` contract object): WindowEd(S) against the measured
-    # integer peak, the traceback against HBM (16-byte entry per visited text column; it is latency-, not bandwidth-bound)
-    others = []
-    if stage_avg.get("ms_windowed_s", 0) > 0 and int_peak:
-        a = 24.0 * st["word_steps_windowed"] / (stage_avg["ms_windowed_s"] * 1e-3) / 1e12
-        others.append({"kernel": "k_windowed21_score (WindowEd(S) bound)", "bound": "int_alu", "achieved": a, "peak": int_peak,
-                       "unit": "T int32-op/s", "frac": a / int_peak, "ms_per_launch": stage_avg["ms_windowed_s"]})
-    if stage_avg.get("ms_align_trace", 0) > 0 and args.workload in ("c1", "c2"):
-        tb = 16.0 * n_pairs * length
-        a = tb / (stage_avg["ms_align_trace"] * 1e-3) / 1e9
-        others.append({"kernel": "k_traceback_thread (BandEd traceback)", "bound": "hbm_latency", "achieved": a, "peak": peaks.get("hbm_gbs"),
-                       "unit": "GB/s", "frac": a / peaks.get("hbm_gbs"), "algorithmic_bytes": tb, "ms_per_launch": stage_avg["ms_align_trace"],
-                       "traffic": ncu_traffic_bytes("k_traceback_thread") if (args.workload == "c2" and n_pairs == 1000000 and args.algo == "quicked") else None})
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "c5":
-        per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000, "c5": 50}[args.workload]
+    # ---- CPU baseline + parity gate: the reference aligns a sample of the very pairs rank 0 timed ----
+    cpu, parity = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import harness
+        per_pair_us = {"c1": 6, "c2": 50, "c3": 1600, "c4": 100000, "c5": 400}[args.workload]
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample or int(max(cores, min(n_pairs, 15e6 * cores / per_pair_us)))
-        v, used, kind, cdt = cpu_reference_arm(length, error, algo_kw, sample, seed=1000)
-        cpu = {"value": v, "unit": unit, "cores": used, "kind": kind,
-               "sample": f"{sample} pairs of the workload, {used} host threads, {cdt:.1f} s"}
+        sample = int(args.cpu_sample or max(cores, min(n_pairs, 15e6 * cores / per_pair_us)))
+        sample = min(sample, n_pairs)
+        harness.cpu_batch_align(pinned, po[:cores], pl[:cores], to[:cores], tl[:cores], cores, **algo_kw)      # warm the libraries
+        t0 = time.perf_counter()
+        kind, _, cpu_scores = harness.cpu_batch_align(pinned, po[:sample], pl[:sample], to[:sample], tl[:sample], cores, want_scores=True, **algo_kw)
+        cdt = time.perf_counter() - t0
+        if world == 1:
+            cpu = {"value": sample / cdt, "unit": unit, "cores": min(cores, sample), "kind": kind,
+                   "sample": f"the first {sample} pairs of the workload, {min(cores, sample)} host threads, {cdt:.1f} s"}
+        ok = status[:sample] >= 0
+        mism = int(np.count_nonzero(cpu_scores[ok] != score[:sample][ok])) + int(np.count_nonzero(~ok))
+        n_replay, bad_cigars = 0, 0
+        if cig is not None:
+            for i in range(0, n_pairs, max(1, n_pairs // 256)):
+                text = bytes(cig[off[i]:off[i + 1] - 1])
+                cost = replay_cigar(text, bytes(pinned[po[i]:po[i] + pl[i]]), bytes(pinned[to[i]:to[i] + tl[i]]))
+                n_replay += 1
+                bad_cigars += int(cost != int(score[i]))
+        parity = {"pairs_checked": sample, "mismatches": mism, "checker": kind, "cigars_replayed": n_replay, "cigar_errors": bad_cigars}
 
     if rank == 0:
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64",
                "data": "synthetic", "config": config,
                "gcups_equiv": value * length * length / 1e9,
-               "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(st_e["h2d_bytes"]),
-                       "d2h_bytes_per_step": int(st_e["d2h_bytes"])},
-               "gpu_launches": int(launches), "host_affinity": numa, "roofline": roof, "int_alu_roofline": int_roof, "other_kernel_rooflines": others, "cpu_baseline": cpu,
+               "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all)},
+               "gpu_launches": int(launches), "host_affinity": numa, "roofline": roof, "int_alu_roofline": int_roof,
+               "hbm_roofline": hbm_roof, "kernel_rooflines": roofs, "cpu_baseline": cpu, "parity": parity,
                "clocks": clocks, "stage_ms_per_step": stage_avg, "dominant_stage": dom,
-               "pairs_ok_fraction": ok_frac, "mean_score": float(score.mean())}
+               "rank_ms_per_step": rank_ms, "imbalance": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
+               "pairs_ok_fraction": ok_frac, "mean_score": float(score.mean()), "leaves_punted": int(st.get("leaves_punted", 0))}
         print(json.dumps(out))
     lib.qb200_host_free(pin); lib.qb200_host_free(cpin)
     gpu.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity and (parity["mismatches"] or parity["cigar_errors"]):
+        sys.stderr.write(f"bench.py: PARITY FAILURE {parity}\n")
+        return 3
     return 0
 
 

@@ -115,6 +115,13 @@ int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, dou
                              char *seqs, int64_t *pattern_off, int32_t *pattern_len,
                              int64_t *text_off, int32_t *text_len);
 
+/* The same generator for pairs [first_pair, first_pair + n_pairs) of job `seed` (every pair has its own random stream,
+ * so ranks can generate disjoint slices of one job), plus the reference's `--indels N,LEN` switch
+ * (generate_dataset.c:204-245: a uniform count in [0, N] of LEN-long deletions).  Offsets are relative to `seqs`. */
+int64_t qb200_generate_pairs_ex(uint64_t seed, int64_t first_pair, int64_t n_pairs, int32_t length, double error,
+                                int32_t indels_num, int32_t indels_len, char *seqs, int64_t *pattern_off,
+                                int32_t *pattern_len, int64_t *text_off, int32_t *text_len);
+
 /* --- SAM-style CIGAR of one alignment (host-side string transform; reference cigar_compute_CIGAR /
  * cigar_sprint_SAM_CIGAR, quicked_utils/src/cigar.c:193-240, :504-529).  `cigar` is the run-length text this library
  * and the reference's quicked_align produce ("12M1X3I...": M match, X mismatch, I consumes a text character,

@@ -201,3 +201,28 @@ def cpu_batch_align(seqs, po, pl, to, tl, threads, algo=0, bandwidth=15, window_
     p = o.params(algo=algo, bandwidth=bandwidth, window_size=window_size, overlap_size=overlap_size, only_score=only_score, force_scalar=force_scalar)
     b = o.lib.qo_batch_align(seqs.ctypes.data, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data, n, int(threads), C.byref(p), sp)
     return "port", int(b), scores
+
+
+def generate_pairs(seed, n_pairs, length, error, first=0, indels=None, threads=None):
+    """Checker-side twin of quicked_b200.generate_pairs_native (oracle/datagen.c: same model, same random streams):
+    pairs [first, first + n_pairs) of job `seed` in the packed layout.  Lets bench.py --impl reference make its data
+    without loading the product library.  -> (seqs, po, pl, to, tl) numpy arrays."""
+    import math
+    import numpy as np
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    L = C.CDLL(ORACLE_SO)
+    L.qo_generate_pairs.restype = C.c_int64
+    L.qo_generate_pairs.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    nerr = int(error) if error >= 1.0 else int(math.ceil(np.float32(length) * np.float32(error)))
+    stride = 2 * length + nerr + 2
+    seqs = np.zeros((n_pairs * stride + 15) // 16 * 16, np.uint8)
+    po = np.zeros(n_pairs, np.int64); to = np.zeros(n_pairs, np.int64)
+    pl = np.zeros(n_pairs, np.int32); tl = np.zeros(n_pairs, np.int32)
+    ind = indels or (0, 0)
+    rc = L.qo_generate_pairs(seed, first, n_pairs, length, float(error), int(ind[0]), int(ind[1]), int(threads or os.cpu_count() or 1),
+                             seqs.ctypes.data, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data)
+    if rc < 0:
+        raise RuntimeError("qo_generate_pairs failed")
+    return seqs, po, pl, to, tl

@@ -39,10 +39,15 @@ static void *worker(void *arg)
     job_t *j = (job_t *)arg;
     mm_allocator_t *mm = mm_allocator_new(1ull << 27);                   /* BUFFER_SIZE_128M, align_benchmark.c:51 */
     j->prm.external_allocator = mm;
+    j->prm.external_timer = true;                                        /* benchmark_edit.c:47: the tool owns the timers */
+    /* five per-thread timers the aligner points at (benchmark_edit.c:61-65); profiler_timer_t is 88 bytes */
+    static __thread unsigned char timers[5][128] __attribute__((aligned(16)));
+    memset(timers, 0, sizeof timers);
     int64_t bytes = 0;
     for (int64_t i = j->lo; i < j->hi; ++i) {
         ref_aligner_t a;
         quicked_new(&a, &j->prm);
+        for (int t = 0; t < 5; ++t) a.timers[t] = timers[t];
         /* NUL-terminated copies are not needed: the packed buffer keeps a byte after every text (see bench.py) */
         quicked_align(&a, j->seqs + j->po[i], j->pl[i], j->seqs + j->to[i], j->tl[i]);
         if (j->score) j->score[i] = a.score;

@@ -26,7 +26,7 @@ EXPORTS = ["quicked_check_error", "quicked_status_msg", "quicked_default_params"
            "quicked_align", "qb200_device_count", "qb200_create", "qb200_destroy", "qb200_set_stream",
            "qb200_set_workspace_limit", "qb200_last_error", "qb200_upload", "qb200_upload_device", "qb200_run",
            "qb200_download", "qb200_get_stats", "qb200_get_bounds", "qb200_cigar_to_sam", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
-           "qb200_generate_pairs", "qb200_measure_int_peak"]
+           "qb200_generate_pairs", "qb200_generate_pairs_ex", "qb200_measure_int_peak"]
 
 
 class Params(C.Structure):        # quicked_params_t, 48 bytes
@@ -319,8 +319,9 @@ def cigar_to_sam(cigar, show_mismatches=False):
     return buf.raw[:n].decode()
 
 
-def generate_pairs_native(seed, n_pairs, length, error):
-    """Seeded generate_dataset twin in C (qb200_generate_pairs).  -> (seqs, po, pl, to, tl) numpy arrays."""
+def generate_pairs_native(seed, n_pairs, length, error, first=0, indels=None):
+    """Seeded generate_dataset twin in C (qb200_generate_pairs_ex): pairs [first, first + n_pairs) of job `seed`,
+    optional indels=(num, length) like the reference's --indels.  -> (seqs, po, pl, to, tl) numpy arrays."""
     import math
     L = load()
     nerr = int(error) if error >= 1.0 else int(math.ceil(np.float32(length) * np.float32(error)))
@@ -329,8 +330,12 @@ def generate_pairs_native(seed, n_pairs, length, error):
     seqs = np.zeros(total, np.uint8)
     po = np.zeros(n_pairs, np.int64); to = np.zeros(n_pairs, np.int64)
     pl = np.zeros(n_pairs, np.int32); tl = np.zeros(n_pairs, np.int32)
-    rc = L.qb200_generate_pairs(seed, n_pairs, length, float(error), seqs.ctypes.data, po.ctypes.data, pl.ctypes.data,
-                                to.ctypes.data, tl.ctypes.data)
+    L.qb200_generate_pairs_ex.restype = C.c_int64
+    L.qb200_generate_pairs_ex.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    ind = indels or (0, 0)
+    rc = L.qb200_generate_pairs_ex(seed, first, n_pairs, length, float(error), int(ind[0]), int(ind[1]), seqs.ctypes.data,
+                                   po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data)
     if rc < 0:
-        raise RuntimeError(f"qb200_generate_pairs rc={rc}")
+        raise RuntimeError(f"qb200_generate_pairs_ex rc={rc}")
     return seqs, po, pl, to, tl

@@ -205,10 +205,14 @@ int64_t qb200_cigar_to_sam(const char *cigar, int show_mismatches, char *out, in
     return need - 1;
 }
 
-int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, double error, char *seqs,
-                             int64_t *pattern_off, int32_t *pattern_len, int64_t *text_off, int32_t *text_len)
+// Pairs [first_pair, first_pair + n_pairs) of the job `seed`: every pair has its own random stream (hash of seed and
+// pair index), so any rank can generate any slice of the same job.  indels_num / indels_len: the reference's
+// `--indels N,LEN` (generate_dataset.c:204-245): a uniform count in [0, N] of LEN-long deletions at uniform positions.
+int64_t qb200_generate_pairs_ex(uint64_t seed, int64_t first_pair, int64_t n_pairs, int32_t length, double error, int32_t indels_num,
+                                int32_t indels_len, char *seqs, int64_t *pattern_off, int32_t *pattern_len, int64_t *text_off,
+                                int32_t *text_len)
 {
-    if (n_pairs < 0 || length <= 0 || !seqs) return QB200_ERR_ARG;
+    if (n_pairs < 0 || first_pair < 0 || length <= 0 || !seqs || indels_num < 0 || indels_len < 0) return QB200_ERR_ARG;
     const int num_errors = error >= 1.0 ? (int)error : (int)std::ceil((double)((float)length * (float)error));   // :370
     const int64_t stride = 2 * (int64_t)length + num_errors + 2;     // fixed slot per pair: pattern then text
     const char alphabet[4] = {'A', 'C', 'G', 'T'};
@@ -218,8 +222,8 @@ int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, dou
     for (unsigned w = 0; w < nt; ++w) {
         th.emplace_back([=]() {
             for (int64_t i = w; i < n_pairs; i += nt) {
-                uint64_t s = seed ^ 0x5851f42d4c957f2dull;            // independent stream per pair: hash (seed, i)
-                s = splitmix64(s) ^ ((uint64_t)i * 0xd6e8feb86659fd93ull);
+                uint64_t s = seed ^ 0x5851f42d4c957f2dull;            // independent stream per pair: hash (seed, index in the job)
+                s = splitmix64(s) ^ ((uint64_t)(first_pair + i) * 0xd6e8feb86659fd93ull);
                 s = splitmix64(s);
                 char *pat = seqs + i * stride, *txt = pat + length + num_errors + 1;
                 for (int k = 0; k < length; ++k) txt[k] = alphabet[rand_below(s, 4)];
@@ -243,6 +247,16 @@ int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, dou
                         ++len;
                     }
                 }
+                if (indels_num > 0 && indels_len > 0) {                // large deletions (:204-245)
+                    const uint32_t cnt = rand_below(s, (uint32_t)indels_num + 1);
+                    for (uint32_t d = 0; d < cnt; ++d) {
+                        const uint32_t pos = rand_below(s, (uint32_t)std::max(len, 1));
+                        if (indels_len >= len) continue;
+                        const int nl = len - indels_len;
+                        if ((int)pos < nl) memmove(pat + pos, pat + pos + indels_len, (size_t)(nl - (int)pos));
+                        len = nl;
+                    }
+                }
                 pat[len] = 0;
                 txt[length] = 0;
                 pattern_off[i] = i * stride; pattern_len[i] = len;
@@ -252,6 +266,12 @@ int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, dou
     }
     for (auto &t : th) t.join();
     return n_pairs * stride;
+}
+
+int64_t qb200_generate_pairs(uint64_t seed, int64_t n_pairs, int32_t length, double error, char *seqs,
+                             int64_t *pattern_off, int32_t *pattern_len, int64_t *text_off, int32_t *text_len)
+{
+    return qb200_generate_pairs_ex(seed, 0, n_pairs, length, error, 0, 0, seqs, pattern_off, pattern_len, text_off, text_len);
 }
 
 }  // extern "C"

@@ -126,6 +126,7 @@ struct qb200_ctx {
     int sms = 0;                           // SM count of the device (queried once)
     DevBuf d_tclass, d_tctl, d_punt, d_gather, d_ttext;   // tile path: per-class task lists, counters, punted tasks
     bool use_tiles = true;
+    int thread_band_max = 4;               // leaves with B_cigar <= this use the thread-per-leaf full-matrix kernels (0: everything through the tile kernels)
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
     bool unknown_algo = false, multi_leaf_pairs = false;
     static constexpr int kWorkers = 8;
@@ -546,6 +547,8 @@ int qb200_create(qb200_ctx_t **out, int device)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return QB200_ERR_CUDA; }
     ctx->own_stream = true;
     if (const char *e = getenv("QB200_TILES")) ctx->use_tiles = atoi(e) != 0;
+    if (const char *e = getenv("QB200_THREAD_BAND_MAX")) ctx->thread_band_max = std::max(0, std::min(atoi(e), (int)kThreadBandMax));
+    if (!ctx->use_tiles) ctx->thread_band_max = kThreadBandMax;
     *out = ctx;
     return 0;
 }
@@ -811,7 +814,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         Span sp(ctx, ST_PLAN);
         PlanParams pp;
         pp.algo = (int)prm.algo; pp.bandwidth = prm.bandwidth; pp.hew_pct0 = prm.hew_percentage[0];
-        pp.only_score = prm.only_score; pp.thread_band_max = kThreadBandMax;
+        pp.only_score = prm.only_score; pp.thread_band_max = ctx->thread_band_max;
         pp.ok_status = (prm.algo == HIRSCHBERG) ? QUICKED_OK : QUICKED_WIP;
         pp.tiles = ctx->use_tiles ? 1 : 0;
         k_plan<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, pp, ctx->d_bound.as<int>(), ctx->d_hew.as<int>(),
@@ -1175,12 +1178,12 @@ int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
         BandTask &t = leaves[i];
         const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
         Bc[i] = (int)g.Bc;
-        if (g.Bc > kThreadBandMax && !rounds_for(g.Bc)) { ctx->err = "leaf band of " + std::to_string(g.Bc) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
-        if (g.Bc <= kThreadBandMax) list_t.push_back((int)i);
+        if (g.Bc > ctx->thread_band_max && !rounds_for(g.Bc)) { ctx->err = "leaf band of " + std::to_string(g.Bc) + " blocks exceeds the supported 11000"; return QB200_ERR_ARG; }
+        if (g.Bc <= ctx->thread_band_max) list_t.push_back((int)i);
         else if (ctx->use_tiles && tile_band_ok(g.Bc)) { list_x.push_back((int)i); xmask |= tile_class_bit(g.Bc); }
         else list_w.push_back((int)i);
         t.range_off = rg; rg += t.n / 64 + 2;
-        t.scores_off = sc; if (g.Bc > kThreadBandMax) sc += (i64)((t.m + 63) / 64) + g.Bc + 2;
+        t.scores_off = sc; if (g.Bc > ctx->thread_band_max) sc += (i64)((t.m + 63) / 64) + g.Bc + 2;
     }
     // chunk plans: (kind: 1 thread kernel, 0 warp kernel, 2 tile kernels; list begin, list end, entries)
     struct Chunk { int thr, q0, q1; i64 ent; };
@@ -1541,7 +1544,7 @@ static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std:
             lf.ops_cap = ((nd.m + nd.n + 15) / 16) * 16; lf.ops_off = ops_words;
             {   // 2-bit ops (thread walk, tile walk); u32 runs, worst case, for the full-matrix warp walk
                 const i64 bc = band_geometry(nd.m, nd.n, nd.cutoff).Bc;
-                ops_words += (bc <= kThreadBandMax || (ctx->use_tiles && tile_band_ok(bc))) ? lf.ops_cap / 16 : lf.ops_cap;
+                ops_words += (bc <= ctx->thread_band_max || (ctx->use_tiles && tile_band_ok(bc))) ? lf.ops_cap / 16 : lf.ops_cap;
             }
             lf.slot = (int)(L0 + (i64)leaves.size());
             if (res[q].pl.n_leaves == 0) res[q].pl.first_leaf = lf.slot;

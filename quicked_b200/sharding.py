@@ -66,3 +66,17 @@ def balanced_ranges(lengths, world, error=0.15):
         bounds.append(len(work))
     bounds.append(len(work))
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def strided_deal(pattern_len, text_len, rank, world, error=0.15):
+    """Indices of rank's share of a mixed-length batch: pairs sorted by estimated work (heaviest first) and dealt
+    round-robin, so every GPU gets the same mix of lengths (BASELINE config 5); results are gathered by index.
+    numpy arrays in, sorted numpy index array out."""
+    import numpy as np
+    m = np.asarray(pattern_len, dtype=np.int64); n = np.asarray(text_len, dtype=np.int64)
+    L = np.maximum(m, n)
+    band = -(-(error * L).astype(np.int64) // 64) + 2
+    split = np.where(band * n * 16 > (1 << 24), 2, 1)
+    work = 4 * n + band * n * split
+    order = np.argsort(-work, kind="stable")
+    return np.sort(order[rank::world])

@@ -147,3 +147,45 @@ def test_cigar_to_sam_matches_reference(reference):
             out = C.create_string_buffer(2 * len(ops) + 16)
             n = ref.cigar_sprint_SAM_CIGAR(out, len(out), C.byref(rc), show)
             assert cigar_to_sam(cig, show) == out.raw[:n].decode(), (cig, show)
+
+
+def test_generator_twin_matches_the_checker_side_generator(lib):
+    """qb200_generate_pairs_ex (product, host code) and oracle/datagen.c (checker side, used by bench.py --impl reference)
+    are the same seeded model: byte-identical pairs, any slice of a job, with and without --indels."""
+    import numpy as np
+    import quicked_b200 as qb
+    from oracle import harness
+    for kw in (dict(first=0), dict(first=12345), dict(first=7, indels=(3, 40))):
+        a = qb.generate_pairs_native(11, 64, 300, 0.1, **kw)
+        b = harness.generate_pairs(11, 64, 300, 0.1, **kw)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    whole = qb.generate_pairs_native(11, 100, 200, 0.2)
+    part = qb.generate_pairs_native(11, 10, 200, 0.2, first=90)
+    for i in range(10):
+        j = 90 + i
+        assert bytes(whole[0][whole[1][j]:whole[1][j] + whole[2][j]]) == bytes(part[0][part[1][i]:part[1][i] + part[2][i]])
+        assert bytes(whole[0][whole[3][j]:whole[3][j] + whole[4][j]]) == bytes(part[0][part[3][i]:part[3][i] + part[4][i]])
+
+
+def test_bench_helpers(oracle):
+    """bench.py's parity gate: the CIGAR replay accepts the oracle's alignments and rejects corrupted ones; the
+    mixed-batch deal covers every pair exactly once and re-packs sequences intact."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import harness
+    from quicked_b200.sharding import strided_deal
+    s, po, pl, to, tl = harness.generate_pairs(5, 24, 500, 0.15)
+    for i in range(24):
+        p, t = bytes(s[po[i]:po[i] + pl[i]]), bytes(s[to[i]:to[i] + tl[i]])
+        st, sc, cg = oracle.align(p, t)
+        assert bench.replay_cigar(cg.encode(), p, t) == sc
+        assert bench.replay_cigar(cg.encode().replace(b"M", b"X", 1), p, t) != sc
+    seen = np.concatenate([strided_deal(pl, tl, r, 5) for r in range(5)])
+    assert sorted(seen.tolist()) == list(range(24))
+    sel = strided_deal(pl, tl, 2, 5)
+    s2, po2, pl2, to2, tl2 = bench.gather_pairs(s, po, pl, to, tl, sel)
+    for j, i in enumerate(sel):
+        assert bytes(s2[po2[j]:po2[j] + pl2[j]]) == bytes(s[po[i]:po[i] + pl[i]])
+        assert bytes(s2[to2[j]:to2[j] + tl2[j]]) == bytes(s[to[i]:to[i] + tl[i]])

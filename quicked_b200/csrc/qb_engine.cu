@@ -421,7 +421,7 @@ int launch_tile_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n, i
 {
     if (n <= 0) return 0;
     k_traceback_tiles<<<(n + kTileTraceThreads - 1) / kTileTraceThreads, kTileTraceThreads, 0, ctx->stream>>>(
-        ctx->d_leaves.as<BandTask>(), d_list, begin, n, sub, ctx->d_codes.as<unsigned char>(), ctx->raw(), peq_base, ctx->d_matrix.as<TileRec>(),
+        ctx->d_leaves.as<BandTask>(), d_list, begin, n, sub, ctx->d_ttext.as<u64>(), ctx->raw(), peq_base, ctx->d_matrix.as<TileRec>(),
         ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>(), ctx->d_punt.as<int>(),
         &ctx->d_tctl.as<TileCtl>()->punt_count);
     CK(cudaGetLastError());

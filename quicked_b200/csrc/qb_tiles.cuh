@@ -632,16 +632,22 @@ __global__ void __launch_bounds__(256) k_tile_text(const BandTask *__restrict__ 
     const int nw = (ncols + 63) / 64 * 8;
     const unsigned char *src = codes + t.t_off;
     u64 *dst = ttext + t.tt_off;
-    for (int w = lane; w <= nw; w += 32) {
+    u32 odd = 0;
+    for (int w = lane; w < nw; w += 32) {
         u64 v = 0;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const int col = 8 * w + b;
-            const unsigned cd = col < ncols ? (unsigned)(src[t.rev ? t.n - 1 - col : col] & 7u) : 4u;
-            v |= (u64)cd << (8 * b);
+            const unsigned raw = col < ncols ? (unsigned)src[t.rev ? t.n - 1 - col : col] : 4u;
+            odd |= raw & kCodeOdd;
+            v |= (u64)(raw & 7u) << (8 * b);
         }
         dst[w] = v;
     }
+    // last word of the task's slot: does the text hold a character outside "ACGTN"? (the tile traceback then compares
+    // raw bytes on diagonal steps, reference bpm_banded.c:1012)
+    odd = __ballot_sync(kFull, odd != 0);
+    if (lane == 0) dst[nw] = odd ? 1ull : 0ull;
 }
 
 }  // namespace qb

@@ -29,8 +29,9 @@ namespace qb {
 constexpr int kTraceCols = 64;        // plane words per thread (one per tile column)
 constexpr int kTraceHalf = 8;         // rows kept on each side of the walk's diagonal
 
-// planes[s * ps]: decision planes of tile column s; eq[c * eqs]: the block's match masks.
-QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ranges, const unsigned char *codes,
+// planes[s * ps]: decision planes of tile column s; eq[c * eqs]: the block's match masks; ttext: the task's aligned text
+// codes (tile-text pool, 8 per u64; its last word flags a text with characters outside "ACGTN").
+QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ranges, const u64 *ttext,
                          const unsigned char *raw, const u64 *peq_pool, u32 *ops, u32 *planes, int ps, u64 *eq, int eqs,
                          LeafOut &o)
 {
@@ -38,7 +39,8 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
     const int B = (int)g.Bc, prolog = (int)g.prolog;
     const int nshift = tk.n >> 6;
     const u64 *pq = peq_pool + tk.peq_off;
-    const unsigned char *tcodes = codes + tk.t_off;
+    const u64 *tt = ttext + tk.tt_off;
+    const bool text_odd = tt[(tk.n + 63) / 64 * 8] != 0;
     const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
     OpWriter w; w.init(ops, tk.ops_cap);
     int h = tk.n - 1, v = tk.m - 1;
@@ -65,23 +67,38 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
         const TileRec rec = recs[(i64)kb * B + j];
         u64 pv = rec.pv0, mv = rec.mv0;
         const int lo0 = r0 - s0 - kTraceHalf;                        // lowest slice row at column 0 (may be negative)
-        u64 colodd = 0;                                              // columns whose text character is outside "ACGTN"
+        // the walk stays within kTraceHalf rows of its diagonal and above row 0: it cannot reach columns below s_need
+        const int s_need = s0 - r0 - kTraceHalf;
+        u32 wp = rec.cin.p0, wm = rec.cin.m0;
+        const u64 *tw = tt + 8 * (i64)kb;
+        u64 cw = tw[0];
 #pragma unroll 1
         for (int s = 0; s <= s0; ++s) {
-            const unsigned cs = tcodes[64 * kb + s];
-            const u64 e = eq[(cs & 7u) * eqs];
-            colodd |= (u64)((cs >> 3) & 1u) << s;
-            const u32 hp = ((s < 32 ? rec.cin.p0 : rec.cin.p1) >> (31 - (s & 31))) & 1u;
-            const u32 hm = ((s < 32 ? rec.cin.m0 : rec.cin.m1) >> (31 - (s & 31))) & 1u;
+            if ((s & 7) == 0 && s) cw = tw[s >> 3];
+            if (s == 32) { wp = rec.cin.p1; wm = rec.cin.m1; }
+            const u64 e = eq[(unsigned)(cw & 7u) * eqs];
+            cw >>= 8;
             const u64 mv_old = mv;
-            u32 d0, d1;
-            myers_step(e, pv, mv, hp, hm, d0, d1);
-            const u64 pa = pv | ~(mv_old | e), pb = ~pv & (mv_old | ~e);
-            const int lo = lo0 + s;
-            u32 sa, sb;
-            if (lo >= 0) { sa = lo < 64 ? (u32)(pa >> lo) : 0u; sb = lo < 64 ? (u32)(pb >> lo) : 0u; }
-            else { sa = -lo < 64 ? (u32)(pa << -lo) : 0u; sb = -lo < 64 ? (u32)(pb << -lo) : 0u; }
-            planes[s * ps] = (sa & 0xffffu) | (sb << 16);
+            {   // Myers block update without carry-outs (the record holds the tile's carry-ins, top bit first)
+                const u64 xv = e | mv;
+                const u64 eqh = e | (u64)(wm >> 31);
+                const u64 xh = (((eqh & pv) + pv) ^ pv) | eqh;
+                u64 ph = mv | ~(xh | pv);
+                u64 mh = pv & xh;
+                ph = (ph << 1) | (u64)(wp >> 31);
+                mh = (mh << 1) | (u64)(wm >> 31);
+                wp <<= 1; wm <<= 1;
+                pv = mh | ~(xv | ph);
+                mv = ph & xv;
+            }
+            if (s >= s_need) {
+                const u64 pa = pv | ~(mv_old | e), pb = ~pv & (mv_old | ~e);
+                const int lo = lo0 + s;
+                u32 sa, sb;
+                if (lo >= 0) { sa = lo < 64 ? (u32)(pa >> lo) : 0u; sb = lo < 64 ? (u32)(pb >> lo) : 0u; }
+                else { sa = -lo < 64 ? (u32)(pa << -lo) : 0u; sb = -lo < 64 ? (u32)(pb << -lo) : 0u; }
+                planes[s * ps] = (sa & 0xffffu) | (sb << 16);
+            }
         }
         // ---- walk inside the tile ----
         int r = r0, s = s0;
@@ -95,7 +112,7 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
             if (a != bb) op = a ? OP_D : OP_I;
             else {
                 op = a ? OP_X : OP_M;
-                if (((rowodd >> r) | (colodd >> s)) & 1ull)           // odd character: raw bytes decide (bpm_banded.c:1012)
+                if (text_odd || ((rowodd >> r) & 1ull))               // odd character: raw bytes decide (bpm_banded.c:1012)
                     op = (traw[64 * kb + s] == praw[64 * b + r]) ? OP_M : OP_X;
             }
             w.emit(op);
@@ -117,7 +134,7 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
 constexpr int kTileTraceThreads = 128;
 __global__ void __launch_bounds__(kTileTraceThreads)
 k_traceback_tiles(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 rec_sub,
-                  const unsigned char *__restrict__ codes, const unsigned char *__restrict__ raw, const u64 *__restrict__ peq,
+                  const u64 *__restrict__ ttext, const unsigned char *__restrict__ raw, const u64 *__restrict__ peq,
                   const TileRec *__restrict__ recs, const int2 *__restrict__ range_pool, const BandOut *__restrict__ fill_out,
                   u32 *__restrict__ ops_pool, LeafOut *__restrict__ outs, int *__restrict__ punt_list, int *__restrict__ punt_count)
 {
@@ -131,7 +148,7 @@ k_traceback_tiles(const BandTask *__restrict__ tasks, const int *__restrict__ li
     LeafOut o;
     int rc = 3;
     if (fill_out[tk.slot].pos_v != kTilePunted)
-        rc = tile_traceback(tk, recs + (tk.mat_off - rec_sub) / 2, range_pool + tk.range_off, codes, raw, peq, ops_pool + tk.ops_off,
+        rc = tile_traceback(tk, recs + (tk.mat_off - rec_sub) / 2, range_pool + tk.range_off, ttext, raw, peq, ops_pool + tk.ops_off,
                             s_planes + threadIdx.x, kTileTraceThreads, s_eq + threadIdx.x, kTileTraceThreads, o);
     if (rc) { punt_list[atomicAdd(punt_count, 1)] = ti; return; }
     outs[tk.slot] = o;

@@ -61,6 +61,7 @@ struct Emu {
     std::vector<u64> state;
     std::vector<BandOut> outs;
     std::vector<int> punt;
+    std::vector<u64> ttext;
     int punt_count = 0;
 };
 
@@ -94,14 +95,17 @@ static u64 emulate(Emu &E, int RB, int nslots, int L, bool shuffle)
         const int ncols = FULL ? t.n : t.finish;
         const int nw = (ncols + 63) / 64 * 8;
         t.tt_off = (i64)ttext.size();
-        for (int w = 0; w <= nw; ++w) {
+        unsigned odd = 0;
+        for (int w = 0; w < nw; ++w) {
             u64 v = 0;
-            for (int b = 0; b < 8; ++b) { const int col = 8 * w + b; const unsigned cd = col < ncols ? (E.codes[t.t_off + (t.rev ? t.n - 1 - col : col)] & 7u) : 4u; v |= (u64)cd << (8 * b); }
+            for (int b = 0; b < 8; ++b) { const int col = 8 * w + b; const unsigned rawc = col < ncols ? E.codes[t.t_off + (t.rev ? t.n - 1 - col : col)] : 4u; odd |= rawc & 8u; v |= (u64)(rawc & 7u) << (8 * b); }
             ttext.push_back(v);
         }
+        ttext.push_back(odd ? 1 : 0);
     }
+    E.ttext = ttext;
     TilePools P;
-    P.ttext = ttext.data();
+    P.ttext = E.ttext.data();
     P.tasks = E.tasks.data(); P.codes = E.codes.data(); P.peq = E.peq.data(); P.recs = E.recs.data();
     P.ranges = E.ranges.data(); P.scores = E.scores.data(); P.state = E.state.data(); P.outs = E.outs.data();
     P.punt_list = E.punt.data(); P.punt_count = &E.punt_count; P.rec_sub = 0;
@@ -330,7 +334,7 @@ static int check_full_mode(std::vector<Case> &cases, int nslots, int L, int *n_p
             LeafOut lo; memset(&lo, 0, sizeof lo);
             u32 planes[kTraceCols];
             u64 eqs[kAlpha];
-            const int rc = tile_traceback(t, E.recs.data() + t.mat_off / 2, E.ranges.data() + t.range_off, E.codes.data(), E.raw.data(), E.peq.data(),
+            const int rc = tile_traceback(t, E.recs.data() + t.mat_off / 2, E.ranges.data() + t.range_off, E.ttext.data(), E.raw.data(), E.peq.data(),
                                           ops.data(), planes, 1, eqs, 1, lo);
             if (rc != 0) { if (n_punt_trace) ++*n_punt_trace; }
             else {

@@ -35,7 +35,10 @@ typedef struct qb200_ctx qb200_ctx_t;
 
 /* A batch of pairs: sequence i is seqs[off[i] .. off[i]+len[i]).  Mirrors sequence_buffer_t
  * (reference sequence_buffer.h:30-50): one packed character buffer plus per-pair offsets and lengths.
- * Bytes are raw ASCII exactly as the reference takes them (dna_encode semantics, reference dna_text.c:41-46). */
+ * Bytes are raw ASCII exactly as the reference takes them (dna_encode semantics, reference dna_text.c:41-46).
+ * At most 2^31 - 2^20 pairs per batch.  Big jobs are pipelined in sub-batches that upload the byte range spanned by
+ * their pairs: keep pattern i and text i close to each other (as sequence_buffer_t does); layouts such as "all
+ * patterns, then all texts" still work but every sub-batch then uploads nearly the whole buffer. */
 typedef struct {
     const char    *seqs;          /* packed characters                                   */
     int64_t        seqs_bytes;

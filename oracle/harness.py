@@ -23,6 +23,8 @@ def build(ref=True):
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
     if ref:
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        # the reference's unmodified callers on the product library (drop-in evidence, tests/test_reference_callers.py)
+        subprocess.run(["make", "-s", "-C", HERE, "refcallers"], check=True)
 
 
 class QoParams(C.Structure):

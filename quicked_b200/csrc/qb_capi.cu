@@ -15,9 +15,48 @@
 
 namespace {
 
-std::mutex g_mu;
-qb200_ctx_t *g_ctx = nullptr;
-bool g_ctx_failed = false;
+// One engine context PER CALLING THREAD (reference threading model, SURVEY §8b: aligners are not thread-safe but
+// different aligners run concurrently — align_benchmark keeps one per OpenMP thread, align_benchmark.c:246-284).
+// A context is created on a thread's first quicked_align, handed back to a process-wide pool when the thread ends and
+// reused by later threads; nothing is destroyed at process exit (the CUDA runtime may already be gone by then).
+// QUICKED_B200_DEVICE = <n> (default 0) pins every thread to one GPU, "all" deals threads round-robin over the GPUs.
+struct CtxPool {
+    std::mutex mu;
+    std::vector<qb200_ctx_t *> idle;
+    int next_dev = 0;
+    bool failed = false;
+};
+CtxPool &ctx_pool() { static CtxPool *p = new CtxPool; return *p; }
+
+struct ThreadCtx {
+    qb200_ctx_t *ctx = nullptr;
+    ~ThreadCtx()
+    {
+        if (!ctx) return;
+        CtxPool &p = ctx_pool();
+        std::lock_guard<std::mutex> lock(p.mu);
+        p.idle.push_back(ctx);
+    }
+};
+thread_local ThreadCtx t_ctx;
+
+qb200_ctx_t *thread_context()
+{
+    if (t_ctx.ctx) return t_ctx.ctx;
+    CtxPool &p = ctx_pool();
+    std::lock_guard<std::mutex> lock(p.mu);
+    if (!p.idle.empty()) { t_ctx.ctx = p.idle.back(); p.idle.pop_back(); return t_ctx.ctx; }
+    if (p.failed) return nullptr;
+    int dev = 0;
+    if (const char *e = getenv("QUICKED_B200_DEVICE")) {
+        if (!strcmp(e, "all")) { const int n = qb200_device_count(); dev = n > 0 ? (p.next_dev++ % n) : 0; }
+        else dev = atoi(e);
+    }
+    qb200_ctx_t *c = nullptr;
+    if (qb200_create(&c, dev) != 0) { p.failed = true; return nullptr; }
+    t_ctx.ctx = c;
+    return c;
+}
 
 // counter_add semantics of the reference (profiler_counter.c:53-73): total, samples, min, max, running mean/var
 void timer_add_sample(profiler_timer_t *t, uint64_t ns)
@@ -107,12 +146,7 @@ quicked_status_t quicked_align(quicked_aligner_t *aligner, const char *pattern, 
     const quicked_params_t *prm = aligner->params;
     if (prm->algo != QUICKED && prm->algo != BANDED && prm->algo != WINDOWED && prm->algo != HIRSCHBERG)
         return QUICKED_UNKNOWN_ALGO;
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_ctx && !g_ctx_failed) {
-        int dev = 0;
-        if (const char *e = getenv("QUICKED_B200_DEVICE")) dev = atoi(e);
-        if (qb200_create(&g_ctx, dev) != 0) { g_ctx = nullptr; g_ctx_failed = true; }
-    }
+    qb200_ctx_t *g_ctx = thread_context();
     if (!g_ctx) {
         fprintf(stderr, "quicked_b200: no CUDA device available; this library has no CPU fallback\n");
         return QUICKED_ERROR;

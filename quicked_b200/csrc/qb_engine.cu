@@ -95,6 +95,8 @@ template <class T> struct PinnedArray {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = n = 0; }
 };
 
+constexpr i64 kMaxPairs = (1ll << 31) - (1ll << 20);   // pair / leaf indices, grid sizes and list offsets are 32-bit
+
 enum Stage { ST_PREP = 0, ST_WS, ST_WL, ST_BANDED, ST_FILL, ST_TRACE, ST_CIGAR, ST_PLAN, ST_FUSED, ST_COUNT };
 
 }  // namespace
@@ -606,14 +608,16 @@ void qb200_host_free(void *p) { if (p) cudaFreeHost(p); }
 int qb200_upload(qb200_ctx_t *ctx, const qb200_batch_t *b)
 {
     if (!ctx || !b || b->n_pairs < 0 || b->seqs_bytes < 0) return QB200_ERR_ARG;
+    if (b->n_pairs > kMaxPairs) { ctx->err = "a batch holds at most 2^31 - 2^20 pairs: split it"; return QB200_ERR_ARG; }
+    if (b->n_pairs > 0 && (!b->pattern_off || !b->pattern_len || !b->text_off || !b->text_len || (b->seqs_bytes > 0 && !b->seqs))) return QB200_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     ctx->n_pairs = b->n_pairs; ctx->raw_bytes = b->seqs_bytes; ctx->d_raw_ext = nullptr;
     memset(&ctx->stats, 0, sizeof ctx->stats);
     // the characters go first: from pinned memory the copy runs while the host builds the pair records below
-    const size_t padded = ((size_t)b->seqs_bytes + 15) / 16 * 16 + 32;
+    const size_t padded = ((size_t)b->seqs_bytes + 15) / 16 * 16 + 48;       // >= 48: the zeroed tail never starts before the buffer
     CK(ctx->d_raw.reserve(padded));
     CK(cudaMemsetAsync(ctx->d_raw.as<char>() + (padded - 48), 0, 48, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_raw.p, b->seqs, (size_t)b->seqs_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (b->seqs_bytes > 0) CK(cudaMemcpyAsync(ctx->d_raw.p, b->seqs, (size_t)b->seqs_bytes, cudaMemcpyHostToDevice, ctx->stream));
     int rc = build_pair_records(ctx, b->n_pairs, b->pattern_off, b->pattern_len, b->text_off, b->text_len, b->seqs_bytes);
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
     ctx->stats.h2d_bytes += b->seqs_bytes;
@@ -623,6 +627,7 @@ int qb200_upload(qb200_ctx_t *ctx, const qb200_batch_t *b)
 int qb200_upload_device(qb200_ctx_t *ctx, const qb200_batch_t *b)
 {
     if (!ctx || !b || b->n_pairs < 0 || b->seqs_bytes < 0) return QB200_ERR_ARG;
+    if (b->n_pairs > kMaxPairs) { ctx->err = "a batch holds at most 2^31 - 2^20 pairs: split it"; return QB200_ERR_ARG; }
     CK(cudaSetDevice(ctx->device));
     const i64 n = b->n_pairs;
     std::vector<int64_t> po((size_t)n), to((size_t)n);
@@ -1560,6 +1565,7 @@ static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std:
             else res[q].status = ok_status;                                                                   // QUICKED ignores it (:290)
             if (!bad[q] && res[q].pl.n_leaves == 0) { res[q].score = 0; res[q].set_score = 1; }               // empty op list
         }
+        if (L0 + (i64)leaves.size() > kMaxPairs) { ctx->err = "more than 2^31 alignment leaves in one batch: split it"; return QB200_ERR_ARG; }
         int rc = build_tables(ctx, jobs);
         if (rc) return rc;
         for (size_t k = 0; k < leaves.size(); ++k) leaves[k].peq_off = jobs[k].peq_off;
@@ -1695,6 +1701,16 @@ int qb200_measure_int_peak(qb200_ctx_t *ctx, double *tera_ops_per_s)
 static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res)
 {
     const i64 n = b->n_pairs;
+    if (n > kMaxPairs) { ctx->err = "a batch holds at most 2^31 - 2^20 pairs: split it"; return QB200_ERR_ARG; }
+    // the sub-batches below are byte ranges [min offset, max end) of the caller's buffer with offsets rebased to them, so
+    // a pair that lies outside the buffer must be caught HERE (build_pair_records would only see the rebased offsets)
+    for (i64 i = 0; i < n; ++i) {
+        const i64 p0 = b->pattern_off[i], t0 = b->text_off[i], m = b->pattern_len[i], tn = b->text_len[i];
+        if (m < 0 || tn < 0 || p0 < 0 || t0 < 0 || p0 + m > b->seqs_bytes || t0 + tn > b->seqs_bytes) {
+            ctx->err = "pair " + std::to_string(i) + ": offsets/lengths outside the packed buffer";
+            return QB200_ERR_ARG;
+        }
+    }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     i64 sub = (i64)sms * kWsResidentCtas * kWsThreads * 2;

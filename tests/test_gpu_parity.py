@@ -452,3 +452,74 @@ def test_large_batch_properties(gpu):
     for i in range(0, n, 4999):
         j = n - 1 - i
         assert t2[off2[i]:off2[i + 1]] == text[off[j]:off[j + 1]]
+
+
+def test_concurrent_aligners_from_many_threads(oracle):
+    """quicked_align from several host threads at once (one aligner per thread, like the reference's OpenMP batch loop,
+    align_benchmark.c:246-284): every thread has its own engine context, no global lock, results stay exact"""
+    import threading
+    import quicked_b200 as qb
+    pairs = generate_pairs(48, 400, 0.1, seed=4242) + generate_pairs(8, 3000, 0.15, seed=4243)
+    want = [oracle.align(p, t) for p, t in pairs]
+    got = [None] * len(pairs)
+    errors = []
+
+    def worker(tid, nthreads):
+        try:
+            a = qb.QuickedAligner()
+            for i in range(tid, len(pairs), nthreads):
+                a.align(pairs[i][0], pairs[i][1])
+                got[i] = (a.getScore(), a.getCigar())
+        except Exception as e:      # pragma: no cover
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(t, 6)) for t in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    for g, w in zip(got, want):
+        assert g == (w[1], w[2])
+
+
+def test_bad_offsets_are_rejected_on_the_pipelined_path(gpu, monkeypatch):
+    """a pair outside the caller's buffer is QB200_ERR_ARG on the resident AND on the pipelined path (which slices the
+    buffer per sub-batch and must not read past it)"""
+    import ctypes as C
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_PIPELINE_MIN_PAIRS", "64")
+    monkeypatch.setenv("QB200_SUB_PAIRS", "1024")
+    n = 5000
+    seqs, po, pl, to, tl = qb.generate_pairs_native(6, n, 100, 0.05)
+    lib = qb.load()
+    score = np.empty(n, np.int32); status = np.empty(n, np.int32); off = np.zeros(n + 1, np.int64)
+    cig = np.zeros(1 << 22, np.uint8)
+    p = qb.make_params(algo=0)
+    for bad_index, field, value in ((4321, "to", int(seqs.size) - 10), (17, "po", -5), (n - 1, "tl", -1)):
+        po2, to2, tl2 = po.copy(), to.copy(), tl.copy()
+        {"to": to2, "po": po2, "tl": tl2}[field][bad_index] = value
+        batch = qb.capi.Batch(seqs.ctypes.data, int(seqs.size), n, po2.ctypes.data, pl.ctypes.data, to2.ctypes.data, tl2.ctypes.data)
+        res = qb.capi.Results(score.ctypes.data, status.ctypes.data, cig.ctypes.data, int(cig.size), off.ctypes.data, 0)
+        assert lib.qb200_align_batch(gpu._h, C.byref(p), C.byref(batch), C.byref(res)) == qb.capi.QB200_ERR_ARG
+    batch = qb.capi.Batch(seqs.ctypes.data, int(seqs.size), n, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data)
+    res = qb.capi.Results(score.ctypes.data, status.ctypes.data, cig.ctypes.data, int(cig.size), off.ctypes.data, 0)
+    assert lib.qb200_align_batch(gpu._h, C.byref(p), C.byref(batch), C.byref(res)) == 0
+
+
+def test_empty_upload_and_workspace_smaller_than_one_group(oracle, monkeypatch):
+    """qb200_upload of an empty batch (0 pairs, 0 bytes) is fine; a workspace limit below the traceback state of a single
+    32-leaf thread group makes the engine grow the pool for that chunk (or fail with QB200_ERR_OOM) instead of
+    writing past it"""
+    import ctypes as C
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_FUSED", "0")
+    lib = qb.load()
+    a = qb.BatchAligner(device=0, workspace_limit=1 << 20)
+    empty = qb.capi.Batch(None, 0, 0, None, None, None, None)
+    assert lib.qb200_upload(a._h, C.byref(empty)) == 0
+    pairs = generate_pairs(200, 1000, 0.1, seed=77)          # one thread group alone: 32 x 1001 x 3 entries = 1.5 MB
+    got = a.align(pairs, algo=0)
+    for (p, t), g in zip(pairs, got):
+        assert g == oracle.align(p, t)
+    a.close()

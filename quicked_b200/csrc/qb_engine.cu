@@ -130,7 +130,7 @@ struct qb200_ctx {
     bool use_tiles = true;
     int thread_band_max = 4;               // leaves with B_cigar <= this use the thread-per-leaf full-matrix kernels (0: everything through the tile kernels)
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
-    bool unknown_algo = false, multi_leaf_pairs = false;
+    bool unknown_algo = false, multi_leaf_pairs = false, tile_walks = false;   // tile_walks: some leaf's text length is still to be measured
     static constexpr int kWorkers = 8;
     qb200_ctx *child[kWorkers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // workers of the pipelined qb200_align_batch
     std::vector<int> h_score, h_status;
@@ -422,6 +422,7 @@ inline unsigned tile_class_bit(i64 B)
 int launch_tile_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base)
 {
     if (n <= 0) return 0;
+    ctx->tile_walks = true;
     k_traceback_tiles<<<(n + kTileTraceThreads - 1) / kTileTraceThreads, kTileTraceThreads, 0, ctx->stream>>>(
         ctx->d_leaves.as<BandTask>(), d_list, begin, n, sub, ctx->d_ttext.as<u64>(), ctx->raw(), peq_base, ctx->d_matrix.as<TileRec>(),
         ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>(), ctx->d_punt.as<int>(),
@@ -673,7 +674,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.h2d_bytes = h2d; ctx->stats.n_pairs = n; ctx->stats.cells = ctx->cells;
     ctx->ev_used = 0; ctx->ev_spans.clear();
-    ctx->have_cigar = false; ctx->cigar_total = 0; ctx->unknown_algo = false; ctx->multi_leaf_pairs = false;
+    ctx->have_cigar = false; ctx->cigar_total = 0; ctx->unknown_algo = false; ctx->multi_leaf_pairs = false; ctx->tile_walks = false;
     if (n == 0) { ctx->ran = true; return 0; }
     if (prm.algo != QUICKED && prm.algo != BANDED && prm.algo != WINDOWED && prm.algo != HIRSCHBERG) {
         ctx->unknown_algo = true;                                   // quicked.c:433: every pair -> QUICKED_UNKNOWN_ALGO
@@ -1008,7 +1009,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
         if (want_cigar) {
-            if (ctx->multi_leaf_pairs) {
+            if (ctx->multi_leaf_pairs || ctx->tile_walks) {
                 CK(ctx->d_textlen.reserve((size_t)n * 4));
                 k_cigar_text<false><<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leaves.as<BandTask>(),
                     ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), ctx->d_textlen.as<int>(), nullptr, nullptr);

@@ -187,8 +187,8 @@ k_pair_finish(const PairLeaves *__restrict__ pl, int n, const LeafOut *__restric
         int s = 0;
         for (int l = 0; l < p.n_leaves; ++l) s += lo[p.first_leaf + l].cost;
         score[i] = s;                                      // cigar_score_edit, quicked.c:54
-        if (p.n_leaves == 1) tb += lo[p.first_leaf].text_len;
-        else tb = -1;                                      // measured by k_cigar_text<false>
+        if (p.n_leaves == 1 && lo[p.first_leaf].text_len >= 0) tb += lo[p.first_leaf].text_len;
+        else tb = -1;                                      // measured by k_cigar_text<false> (several leaves, or a tile walk)
     }
     if (want_cigar) text_bytes[i] = tb;
 }

@@ -42,7 +42,7 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
     const u64 *tt = ttext + tk.tt_off;
     const bool text_odd = tt[(tk.n + 63) / 64 * 8] != 0;
     const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
-    OpWriter w; w.init(ops, tk.ops_cap);
+    LeanWriter w; w.init(ops, tk.ops_cap);
     int h = tk.n - 1, v = tk.m - 1;
     int eq_block = -1;
     u64 rowodd = 0;
@@ -125,7 +125,7 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
     while (h >= 0) { w.emit(OP_I); --h; }
     while (v >= 0) { w.emit(OP_D); --v; }
     w.finish();
-    o.n_ops = tk.ops_cap - w.pos; o.cost = w.cost; o.text_len = w.text_len; o.fmt = 0; o.pad_ = 0;
+    o.n_ops = tk.ops_cap - w.pos; o.cost = w.cost; o.text_len = -1; o.fmt = 0; o.pad_ = 0;      // text length: k_cigar_text<false>
     return 0;
 }
 

@@ -39,6 +39,24 @@ struct OpWriter {
     }
 };
 
+// The tile walk's writer: 2-bit ops and the edit cost only.  The run-length bookkeeping of OpWriter (~8 instructions on
+// the walk's one-op-per-iteration critical path) moves to k_cigar_text's measuring pass, which finds run boundaries
+// 16 ops at a time with one XOR (LeafOut.text_len = -1 asks for it).
+struct LeanWriter {
+    u32 *words;
+    int pos, cost;
+    u32 acc;
+    __host__ __device__ __forceinline__ void init(u32 *w, int cap) { words = w; pos = cap; acc = 0; cost = 0; }
+    __host__ __device__ __forceinline__ void emit(int op)
+    {
+        --pos;
+        acc |= (u32)op << (2 * (pos & 15));
+        if ((pos & 15) == 0) { words[pos >> 4] = acc; acc = 0; }
+        cost += (op != OP_M);
+    }
+    __host__ __device__ __forceinline__ void finish() { if (pos & 15) words[pos >> 4] = acc; }
+};
+
 // Was band word `w` of stored column `c` ever written by the fill?  Column c (state after c text columns) was written
 // with the live range of column block (c-1)/64; a column with c%64==0 is stored after the shift, i.e. with the next
 // block's first and the previous block's last (bpm_banded.c:279-287).  Never-written cells read as 0, which is what
@@ -362,7 +380,7 @@ k_cigar_text(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask *__r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const PairLeaves p = pl[i];
-    if (!WRITE && p.n_leaves < 2) return;        // single-leaf lengths come from the traceback itself
+    if (!WRITE && (p.n_leaves < 1 || (p.n_leaves == 1 && leaf_out[p.first_leaf].text_len >= 0))) return;   // the walk already measured it
     if (WRITE && p.n_leaves == 0) return;        // empty string: the buffer is pre-zeroed
     TextSink sink;
     if (WRITE) sink.init(cigar + cigar_off[i]);

@@ -29,6 +29,7 @@
 #include "qb_tiles.cuh"
 #include "qb_tiletrace.cuh"
 #include "qb_windowed.cuh"
+#include "qb_wintile.cuh"
 
 using namespace qb;
 
@@ -126,7 +127,7 @@ struct qb200_ctx {
     int max_n = 0, max_m = 0;
     int ws_carve_set[2][2] = {{-1, -1}, {-1, -1}};   // shared-memory carve-out already requested for each WindowEd(S) kernel variant
     int sms = 0;                           // SM count of the device (queried once)
-    DevBuf d_tclass, d_tctl, d_punt, d_gather, d_ttext;   // tile path: per-class task lists, counters, punted tasks
+    DevBuf d_tclass, d_tctl, d_punt, d_gather, d_ttext, d_wintile;   // tile path: per-class task lists, counters, punted tasks
     bool use_tiles = true;
     int thread_band_max = 4;               // leaves with B_cigar <= this use the thread-per-leaf full-matrix kernels (0: everything through the tile kernels)
     DevBuf d_peq2, d_jobs2, d_tasks2, d_wintasks, d_winout, d_winscratch, d_split, d_splitout, d_splitscratch, d_scatter;
@@ -568,7 +569,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
                       &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
                       &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB, &ctx->d_peq2, &ctx->d_jobs2, &ctx->d_tasks2, &ctx->d_wintasks,
-                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter, &ctx->d_tclass, &ctx->d_tctl, &ctx->d_punt, &ctx->d_gather, &ctx->d_ttext})
+                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter, &ctx->d_tclass, &ctx->d_tctl, &ctx->d_punt, &ctx->d_gather, &ctx->d_ttext, &ctx->d_wintile})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     ctx->h_pairs.release();
@@ -1150,19 +1151,50 @@ int run_win_tasks(qb200_ctx *ctx, std::vector<WinTask> &tasks, std::vector<WinOu
     const size_t nt = tasks.size();
     outs.resize(nt);
     if (!nt) return 0;
+    // Tile kernel first (one pair per thread, qb_wintile.cuh); the warp kernel then redoes the tasks it flagged: pairs with
+    // characters outside "ACGTN" and 2-word windows with the SSE quirks.  The warp kernel stores whole windows, so its
+    // scratch is only reserved for a bounded number of tasks at a time.
     i64 scr = 0;
-    for (size_t i = 0; i < nt; ++i) { tasks[i].slot = (int)i; tasks[i].scratch_off = scr; scr += (i64)(64 * tasks[i].W + 3) * tasks[i].W; }
-    CK(ctx->d_winscratch.reserve((size_t)scr * 16 + 64));
+    int Wmax = 1;
+    for (size_t i = 0; i < nt; ++i) { tasks[i].slot = (int)i; tasks[i].scratch_off = scr; scr += (i64)(64 * tasks[i].W + 3) * tasks[i].W; Wmax = std::max(Wmax, tasks[i].W); }
     CK(ctx->d_wintasks.reserve(sizeof(WinTask) * nt));
     CK(ctx->d_winout.reserve(sizeof(WinOut) * nt));
     CK(cudaMemcpyAsync(ctx->d_wintasks.p, tasks.data(), sizeof(WinTask) * nt, cudaMemcpyHostToDevice, ctx->stream));
-    {
+    const bool tiles = ctx->use_tiles && Wmax <= 32;
+    if (tiles) {
+        if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+        const int blocks = (int)std::min<i64>(((i64)nt + kWtThreads - 1) / kWtThreads, (i64)ctx->sms * 4);
+        const i64 nthr = (i64)blocks * kWtThreads, rec_tiles = (i64)Wmax * Wmax;
+        CK(ctx->d_wintile.reserve((size_t)((2 * rec_tiles + Wmax) * nthr) * 16 + 64));
         Span sp(ctx, stage);
-        k_windowed_warp<<<(int)((nt + 3) / 4), 128, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                                                                       ctx->d_peq2.as<u64>(), ctx->d_winscratch.as<ulonglong2>(), ctx->d_ops.as<u32>(),
-                                                                       ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>());
+        if (tasks[0].score_only)
+            k_windowed_tiles<true><<<blocks, kWtThreads, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->d_peq2.as<u64>(),
+                ctx->d_wintile.as<ulonglong2>(), rec_tiles, Wmax, ctx->d_ops.as<u32>(), ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>());
+        else
+            k_windowed_tiles<false><<<blocks, kWtThreads, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->d_peq2.as<u64>(),
+                ctx->d_wintile.as<ulonglong2>(), rec_tiles, Wmax, ctx->d_ops.as<u32>(), ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>());
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
+        ctx->tile_walks = true;                     // their text length is measured by k_cigar_text
+    }
+    {
+        // how many tasks does the warp kernel have to redo?  (none on ACGTN data with W > 2)
+        size_t redo = nt;
+        if (tiles) {
+            CK(cudaMemcpyAsync(outs.data(), ctx->d_winout.p, sizeof(WinOut) * nt, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            redo = 0;
+            for (size_t i = 0; i < nt; ++i) redo += outs[i].hew == kWinPunted;
+        }
+        if (redo) {
+            CK(ctx->d_winscratch.reserve((size_t)scr * 16 + 64));
+            Span sp(ctx, stage);
+            k_windowed_warp<<<(int)((nt + 3) / 4), 128, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                                                                           ctx->d_peq2.as<u64>(), ctx->d_winscratch.as<ulonglong2>(), ctx->d_ops.as<u32>(),
+                                                                           ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>(), tiles ? 1 : 0);
+            CK(cudaGetLastError());
+            ctx->stats.kernel_launches++;
+        }
     }
     CK(cudaMemcpyAsync(outs.data(), ctx->d_winout.p, sizeof(WinOut) * nt, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

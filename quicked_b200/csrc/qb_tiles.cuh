@@ -319,9 +319,10 @@ QB_HD u32 byte_of(u32 w, int i)
 }
 
 // Full tile, carry-out at bit 63.  eq: this lane's five match masks, eq[code * EQS] (EQS = 0: runtime stride eqs);
-// tt: the tile's 64 text codes, 8 per u64 (low byte = first column), from the aligned tile-text pool; w0/w1: its first
-// two chunks, loaded by the caller long before (two chunks stay in flight: an L2 round trip outlasts 8 word-steps).
-template <int EQS>
+// tt: the tile's 64 text codes, 8 per u64 (low byte = first column), chunk c at tt[c * TS] — TS = 1: the aligned
+// tile-text pool in global memory, otherwise a shared-memory staging area; w/wn: its first two chunks, loaded by the
+// caller long before (two chunks stay in flight: an L2 round trip outlasts 8 word-steps).
+template <int EQS, int TS = 1>
 QB_HD void tile_fill64(u64 &pv, u64 &mv, TileCarry &c, const u64 *eq, int eqs, const u64 *tt, u64 w, u64 wn)
 {
     const int st = EQS ? EQS : eqs;
@@ -333,9 +334,9 @@ QB_HD void tile_fill64(u64 &pv, u64 &mv, TileCarry &c, const u64 *eq, int eqs, c
             const u32 w0 = (u32)w, w1 = (u32)(w >> 32);
             w = wn;
 #ifdef __CUDA_ARCH__
-            wn = __ldg(tt + ((half * 4 + it + 2) & 7));
+            wn = (TS == 1) ? __ldg(tt + ((half * 4 + it + 2) & 7)) : tt[((half * 4 + it + 2) & 7) * TS];
 #else
-            wn = tt[(half * 4 + it + 2) & 7];
+            wn = tt[((half * 4 + it + 2) & 7) * TS];
 #endif
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -321,12 +321,14 @@ __global__ void __launch_bounds__(128)
 k_windowed_warp(const WinTask *__restrict__ tasks, int n_tasks, const unsigned char *__restrict__ codes,
                 const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, ulonglong2 *__restrict__ scratch,
                 u32 *__restrict__ ops_pool, WinOut *__restrict__ outs, LeafOut *__restrict__ leaf_outs,
-                u64 *__restrict__ counters)
+                u64 *__restrict__ counters, int only_punted)
 {
     const int lane = threadIdx.x & 31;
     const int id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (id >= n_tasks) return;
     const WinTask tk = tasks[id];
+    // only_punted: the tile kernel (qb_wintile.cuh) went first and flagged the tasks it leaves to this one
+    if (only_punted && outs[tk.slot].hew != -2147483647 - 1) return;
     const int W = tk.W, O = tk.O;
     const u64 *pq = peq + tk.peq_off;
     const unsigned char *tc = codes + tk.t_off, *traw = raw + tk.t_off, *praw = raw + tk.p_off;

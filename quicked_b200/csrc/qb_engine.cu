@@ -790,6 +790,9 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
         const int sms = ctx->sms;
         int ctas = kWsResidentCtas;
+        // one pair per thread and every pair takes about as long: a batch that fits five CTAs per SM in ONE wave runs
+        // better that way than as a full wave plus a nearly empty one (100 k pairs: 10.7 vs 11.2 ms)
+        if (n <= (i64)sms * 5 * kWsThreads * 11 / 10) ctas = 5;
         if (const char *e = getenv("QB200_WS_CTAS")) ctas = std::max(1, std::min(atoi(e), (int)kWsCtasPerSm));
         const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * ctas);   // persistent: one wave
         CK(ctx->d_quad.reserve((size_t)blocks * kWsThreads * kWsQuadSlots * 8));
@@ -1146,8 +1149,9 @@ int run_score_tasks(qb200_ctx *ctx, std::vector<BandTask> &tasks, std::vector<Ba
     return 0;
 }
 
-int run_win_tasks(qb200_ctx *ctx, std::vector<WinTask> &tasks, std::vector<WinOut> &outs, int stage)
+int run_win_tasks(qb200_ctx *ctx, std::vector<WinTask> &tasks, std::vector<WinOut> &outs, int stage, const u64 *peq_base = nullptr)
 {
+    if (!peq_base) peq_base = ctx->d_peq2.as<u64>();
     const size_t nt = tasks.size();
     outs.resize(nt);
     if (!nt) return 0;
@@ -1168,10 +1172,10 @@ int run_win_tasks(qb200_ctx *ctx, std::vector<WinTask> &tasks, std::vector<WinOu
         CK(ctx->d_wintile.reserve((size_t)((2 * rec_tiles + Wmax) * nthr) * 16 + 64));
         Span sp(ctx, stage);
         if (tasks[0].score_only)
-            k_windowed_tiles<true><<<blocks, kWtThreads, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->d_peq2.as<u64>(),
+            k_windowed_tiles<true><<<blocks, kWtThreads, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), peq_base,
                 ctx->d_wintile.as<ulonglong2>(), rec_tiles, Wmax, ctx->d_ops.as<u32>(), ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>());
         else
-            k_windowed_tiles<false><<<blocks, kWtThreads, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->d_peq2.as<u64>(),
+            k_windowed_tiles<false><<<blocks, kWtThreads, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), peq_base,
                 ctx->d_wintile.as<ulonglong2>(), rec_tiles, Wmax, ctx->d_ops.as<u32>(), ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>());
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
@@ -1190,7 +1194,7 @@ int run_win_tasks(qb200_ctx *ctx, std::vector<WinTask> &tasks, std::vector<WinOu
             CK(ctx->d_winscratch.reserve((size_t)scr * 16 + 64));
             Span sp(ctx, stage);
             k_windowed_warp<<<(int)((nt + 3) / 4), 128, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), (int)nt, ctx->d_codes.as<unsigned char>(), ctx->raw(),
-                                                                           ctx->d_peq2.as<u64>(), ctx->d_winscratch.as<ulonglong2>(), ctx->d_ops.as<u32>(),
+                                                                           peq_base, ctx->d_winscratch.as<ulonglong2>(), ctx->d_ops.as<u32>(),
                                                                            ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>(), tiles ? 1 : 0);
             CK(cudaGetLastError());
             ctx->stats.kernel_launches++;
@@ -1332,14 +1336,12 @@ static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std:
     auto pair_of = [&](size_t q) -> const PairRec & { return ctx->h_pairs[(size_t)slow_pairs[q]]; };
 
     if (prm.algo == WINDOWED) {                                             // run_windowed, quicked.c:91-123
-        std::vector<PeqJob> jobs;
         std::vector<WinTask> wt;
         std::vector<size_t> who;
+        wt.reserve(ns); who.reserve(ns); leaves.reserve(ns);
         for (size_t q = 0; q < ns; ++q) {
             const PairRec &r = pair_of(q);
             if (W < 1 || W > 32 || O < 0 || O >= W) { res[q].status = QUICKED_UNIMPLEMENTED; continue; }
-            PeqJob j; j.src_off = r.p_off; j.m = r.m; j.rev = 0; j.peq_off = 0;
-            jobs.push_back(j);
             WinTask t{};
             t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = 0; t.W = W; t.O = O; t.hew_threshold = 0;
             t.sse = sse; t.score_only = prm.only_score; t.nbp = (r.m + 63) / 64 + 2;
@@ -1354,16 +1356,16 @@ static int run_slow_path(qb200_ctx *ctx, const quicked_params_t &prm, const std:
             }
             wt.push_back(t); who.push_back(q);
         }
-        int rc = build_tables(ctx, jobs);
-        if (rc) return rc;
-        for (size_t k = 0; k < wt.size(); ++k) wt[k].peq_off = jobs[k].peq_off;
+        // forward patterns: the match masks of the prepare stage serve as they are (no second table build)
+        for (size_t k = 0; k < wt.size(); ++k) wt[k].peq_off = pair_of(who[k]).peq_off;
+        int rc = 0;
         CK(ctx->d_ops.grow_keep((size_t)std::max<i64>(ops_words, 1) * 4 + 16, (size_t)ops_words_total * 4, ctx->stream));
         CK(ctx->d_leaves.grow_keep(sizeof(BandTask) * (size_t)std::max<i64>(L0 + (i64)leaves.size(), 1), sizeof(BandTask) * (size_t)L0, ctx->stream));
         CK(ctx->d_leafout.grow_keep(sizeof(LeafOut) * (size_t)std::max<i64>(L0 + (i64)leaves.size(), 1), sizeof(LeafOut) * (size_t)L0, ctx->stream));
         if (!leaves.empty())
             CK(cudaMemcpyAsync(ctx->d_leaves.as<BandTask>() + L0, leaves.data(), sizeof(BandTask) * leaves.size(), cudaMemcpyHostToDevice, ctx->stream));
         std::vector<WinOut> wo;
-        rc = run_win_tasks(ctx, wt, wo, ST_WL);
+        rc = run_win_tasks(ctx, wt, wo, ST_WL, ctx->d_peq.as<u64>());
         if (rc) return rc;
         for (size_t k = 0; k < wt.size(); ++k) {
             const size_t q = who[k];

@@ -69,35 +69,39 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
         const int lo0 = r0 - s0 - kTraceHalf;                        // lowest slice row at column 0 (may be negative)
         // the walk stays within kTraceHalf rows of its diagonal and above row 0: it cannot reach columns below s_need
         const int s_need = s0 - r0 - kTraceHalf;
-        u32 wp = rec.cin.p0, wm = rec.cin.m0;
         const u64 *tw = tt + 8 * (i64)kb;
-        u64 cw = tw[0];
+        // eight columns per iteration (a tile has them: columns past s0 are computed for nothing, at most seven)
 #pragma unroll 1
-        for (int s = 0; s <= s0; ++s) {
-            if ((s & 7) == 0 && s) cw = tw[s >> 3];
-            if (s == 32) { wp = rec.cin.p1; wm = rec.cin.m1; }
-            const u64 e = eq[(unsigned)(cw & 7u) * eqs];
-            cw >>= 8;
-            const u64 mv_old = mv;
-            {   // Myers block update without carry-outs (the record holds the tile's carry-ins, top bit first)
-                const u64 xv = e | mv;
-                const u64 eqh = e | (u64)(wm >> 31);
-                const u64 xh = (((eqh & pv) + pv) ^ pv) | eqh;
-                u64 ph = mv | ~(xh | pv);
-                u64 mh = pv & xh;
-                ph = (ph << 1) | (u64)(wp >> 31);
-                mh = (mh << 1) | (u64)(wm >> 31);
-                wp <<= 1; wm <<= 1;
-                pv = mh | ~(xv | ph);
-                mv = ph & xv;
-            }
-            if (s >= s_need) {
-                const u64 pa = pv | ~(mv_old | e), pb = ~pv & (mv_old | ~e);
-                const int lo = lo0 + s;
-                u32 sa, sb;
-                if (lo >= 0) { sa = lo < 64 ? (u32)(pa >> lo) : 0u; sb = lo < 64 ? (u32)(pb >> lo) : 0u; }
-                else { sa = -lo < 64 ? (u32)(pa << -lo) : 0u; sb = -lo < 64 ? (u32)(pb << -lo) : 0u; }
-                planes[s * ps] = (sa & 0xffffu) | (sb << 16);
+        for (int s8 = 0; s8 <= s0; s8 += 8) {
+            u64 cw = tw[s8 >> 3];
+            u32 wp = (s8 < 32 ? rec.cin.p0 : rec.cin.p1) << (s8 & 31), wm = (s8 < 32 ? rec.cin.m0 : rec.cin.m1) << (s8 & 31);
+            const bool want = s8 + 7 >= s_need;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int s = s8 + i;
+                const u64 e = eq[(unsigned)(cw & 7u) * eqs];
+                cw >>= 8;
+                const u64 mv_old = mv;
+                {   // Myers block update without carry-outs (the record holds the tile's carry-ins, top bit first)
+                    const u64 xv = e | mv;
+                    const u64 eqh = e | (u64)(wm >> 31);
+                    const u64 xh = (((eqh & pv) + pv) ^ pv) | eqh;
+                    u64 ph = mv | ~(xh | pv);
+                    u64 mh = pv & xh;
+                    ph = (ph << 1) | (u64)(wp >> 31);
+                    mh = (mh << 1) | (u64)(wm >> 31);
+                    wp <<= 1; wm <<= 1;
+                    pv = mh | ~(xv | ph);
+                    mv = ph & xv;
+                }
+                if (want) {
+                    const u64 pa = pv | ~(mv_old | e), pb = ~pv & (mv_old | ~e);
+                    const int lo = lo0 + s;
+                    u32 sa, sb;
+                    if (lo >= 0) { sa = lo < 64 ? (u32)(pa >> lo) : 0u; sb = lo < 64 ? (u32)(pb >> lo) : 0u; }
+                    else { sa = -lo < 64 ? (u32)(pa << -lo) : 0u; sb = -lo < 64 ? (u32)(pb << -lo) : 0u; }
+                    planes[s * ps] = (sa & 0xffffu) | (sb << 16);
+                }
             }
         }
         // ---- walk inside the tile ----

@@ -353,7 +353,11 @@ k_banded_warp_dyn(const BandTask *__restrict__ tasks, const int *__restrict__ li
 // BMAX*5 shared-memory slots, stride T.
 constexpr int kThreadLeafWordStride = 32;   // entries between consecutive band words of a thread-kernel leaf (= lanes per group)
 constexpr int kThreadFillThreads = 128;     // threads per CTA of every kernel that calls banded_thread_fill
-template <int BMAX>
+// REC: instead of the reference's matrix (one (Pv,Mv) entry per word-step, bpm_banded.c:139-140) the fill writes the
+// TILE RECORDS of qb_tiles.cuh — per 64 columns and live block the block's state at the first column and the 64
+// carry-in pairs it received, 32 bytes — which is all the tile traceback (qb_tiletrace.cuh) needs: `mat` then points at
+// the leaf's records (TileRec[k * B + band word], as ulonglong2 pairs).  16 B per word-step become 0.5 B.
+template <int BMAX, bool REC = false>
 __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int rev, const u64 *__restrict__ pq, int nbp,
                                                    const unsigned char *__restrict__ tcodes, ulonglong2 *mat, i64 cs, i64 wsd_,
                                                    int2 *ranges, i64 rstride, u64 *s_eq, int T_, u64 &ws)
@@ -370,10 +374,11 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
         int first = prolog, last = B - 1, pos_v = -prolog, pos_h = 0;
         u64 pv[BMAX], mv[BMAX];
         int sc[BMAX];
+        u64 cwp[REC ? BMAX : 1], cwm[REC ? BMAX : 1];     // REC: the carry-ins of each block over the current 64 columns, first column in the top bit
 #pragma unroll
         for (int j = 0; j < BMAX; ++j) {
             pv[j] = ~0ull; mv[j] = 0ull; sc[j] = 64 * (j + pos_v + 1);            // scores[blk] = 64(blk+1)
-            if (j < B) mat[j * wsd] = make_ulonglong2(~0ull, 0ull);               // column 0
+            if (!REC && j < B) mat[j * wsd] = make_ulonglong2(~0ull, 0ull);       // column 0
         }
         ranges[0] = make_int2(first, last);
         // forward text: aligned 16-byte view of the codes (the flat buffer keeps >= 48 readable bytes past its end)
@@ -410,6 +415,14 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
             st_hi = max(st_hi, last);
             // band index of the last pattern block when its carry-out sits below bit 63 (level_mask, bpm_banded.c:88-102)
             const int jl = mmod ? (nblk - 1 - pos_v) : -1;
+            if (REC) {       // the state every live block starts this column block with
+                ulonglong2 *rec = mat + 2 * ((i64)(col0 >> 6) * B);
+#pragma unroll
+                for (int j = 0; j < BMAX; ++j) {
+                    if (j >= first && j <= last) rec[2 * j] = make_ulonglong2(pv[j], mv[j]);
+                    cwp[j] = 0ull; cwm[j] = 0ull;
+                }
+            }
             // eight columns per loop body (the body has to stay well inside the 32 KB instruction cache); their codes
             // come from one aligned 16-byte load per 16 columns, realigned in registers, two chunks ahead in flight
             uint4 cr = make_uint4(0, 0, 0, 0);
@@ -436,25 +449,35 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
                 for (int k = 0; k < 8; ++k) {
                     if (c0 + k < nc) {
                         const int code = (int)(((k < 4 ? w0 : w1) >> (8 * (k & 3))) & 7u);
-                        ulonglong2 *dst = mat + (i64)(col0 + c0 + k + 1) * cs;
+                        ulonglong2 *dst = REC ? nullptr : mat + (i64)(col0 + c0 + k + 1) * cs;
                         u32 hp = 1, hm = 0;
 #pragma unroll
                         for (int j = 0; j < BMAX; ++j) {
                             if (j >= first && j <= last) {
                                 u32 hpo, hmo;
                                 u64 phr, mhr;
+                                if (REC) { cwp[j] = (cwp[j] << 1) | (u64)hp; cwm[j] = (cwm[j] << 1) | (u64)hm; }
                                 myers_step_hv(s_eq[(j * kAlpha + code) * T], pv[j], mv[j], hp, hm, hpo, hmo, phr, mhr);
                                 int d = (int)hpo - (int)hmo;
                                 if (j == jl) d = (int)((phr >> (mmod - 1)) & 1ull) - (int)((mhr >> (mmod - 1)) & 1ull);
                                 sc[j] += d;
                                 hp = hpo; hm = hmo;
-                                dst[j * wsd] = make_ulonglong2(pv[j], mv[j]);
+                                if (!REC) dst[j * wsd] = make_ulonglong2(pv[j], mv[j]);
                             }
                         }
                     }
                 }
             }
             ws += (u64)max(last - first + 1, 0) * nc;
+            if (REC) {       // the carry-ins of the column block, left-aligned when it is a short one (TileCarry: steps 0..31 | 32..63)
+                ulonglong2 *rec = mat + 2 * ((i64)(col0 >> 6) * B);
+#pragma unroll
+                for (int j = 0; j < BMAX; ++j)
+                    if (j >= first && j <= last) {
+                        const u64 p = nc < 64 ? cwp[j] << (64 - nc) : cwp[j], q = nc < 64 ? cwm[j] << (64 - nc) : cwm[j];
+                        rec[2 * j + 1] = make_ulonglong2((p >> 32) | (p << 32), (q >> 32) | (q << 32));
+                    }
+            }
             if (nc < 64) break;
             // ---- end of a 64-column block (bpm_banded.c:264-301) ----
             int s_f1 = 0, s_l1 = 0, s_l = 0;            // scores[first+1], scores[last-1], scores[last] (band-relative)
@@ -475,7 +498,7 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
                 if (j == last) { pv[j] = ~0ull; mv[j] = 0ull; sc[j] = s_l + 64; }
             // column col0+64 re-stored in the next block's coordinates (the pre-shift store above stays underneath,
             // exactly like the reference's in-place shift, bpm_banded.c:279-287)
-            {
+            if (!REC) {
                 ulonglong2 *dst = mat + (i64)(col0 + 64) * cs;
 #pragma unroll
                 for (int j = 0; j < BMAX; ++j)
@@ -500,7 +523,7 @@ __device__ __forceinline__ void banded_thread_fill(int m, int n, i64 cutoff, int
 // The lane's 5 match masks per live block sit in shared memory ([slot][thread], conflict-free); at every 64-column
 // band shift they move up one slot and only the block that enters the band is fetched (3 x 16 B from the
 // [block][6] table); the per-column fetch is an LDS indexed by the column's code.
-template <int BMAX>
+template <int BMAX, bool REC = false>
 __global__ void __launch_bounds__(128, 5)
 k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 mat_sub,
                 const unsigned char *__restrict__ codes, const u64 *__restrict__ peq, ulonglong2 *__restrict__ matrix,
@@ -514,7 +537,7 @@ k_banded_thread(const BandTask *__restrict__ tasks, const int *__restrict__ list
     if (id < n_tasks) {
         BandTask tk = tasks[list ? list[begin + id] : begin + id];
         tk.mat_off -= mat_sub;
-        banded_thread_fill<BMAX>(tk.m, tk.n, tk.cutoff, tk.rev, peq + tk.peq_off, tk.nbp, codes + tk.t_off, matrix + tk.mat_off,
+        banded_thread_fill<BMAX, REC>(tk.m, tk.n, tk.cutoff, tk.rev, peq + tk.peq_off, tk.nbp, codes + tk.t_off, matrix + tk.mat_off,
                                  tk.mat_cs, tk.mat_ws, range_pool + tk.range_off, 1, s_eq, T, ws);
     }
 #pragma unroll

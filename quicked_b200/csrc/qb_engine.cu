@@ -304,13 +304,13 @@ constexpr int kTileBandMax = kTileMaxRing - 2;      // widest band (blocks) the 
 
 constexpr int kThreadBandMax = 4;
 
-int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base = nullptr)
+int launch_thread_fill(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, i64 mat_sub, const u64 *peq_base = nullptr, bool records = false)
 {
     if (n_tasks <= 0) return 0;
     if (!peq_base) peq_base = ctx->d_peq.as<u64>();
     const int T = kThreadFillThreads;
     const size_t smem = (size_t)kThreadBandMax * kAlpha * T * 8;
-    auto kern = k_banded_thread<kThreadBandMax>;
+    auto kern = records ? k_banded_thread<kThreadBandMax, true> : k_banded_thread<kThreadBandMax, false>;
     if (const char *e = getenv("QB200_FILL_CARVE")) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
     kern<<<(n_tasks + T - 1) / T, T, smem, ctx->stream>>>(
         ctx->d_leaves.as<BandTask>(), d_list, begin, n_tasks, mat_sub, ctx->d_codes.as<unsigned char>(), peq_base,
@@ -376,23 +376,42 @@ int launch_tiles_class(qb200_ctx *ctx, const TilePools &P, int c, int cap, int n
 // BandEd fill of tasks[list[begin .. begin+n)] by the tile kernels, one launch per band-height class in class_mask.
 // FULL: writes tile records (pool d_matrix, task.mat_off in 16-byte units) + live ranges; !FULL: score-only passes.
 // Tasks the kernels give up on: FULL -> BandOut.pos_v = kTilePunted; !FULL -> appended to d_punt (count in d_tctl).
+// Per-launch set-up of the tile kernels for tasks[list[begin .. begin+n)]: band-height class lists and, for every task,
+// its aligned text in the tile-text pool (task.tt_off).  first: this is the first tile work of a fill phase — the text
+// pool and the punt list start empty (several calls of one phase share both: thread-fill leaves, then the wider ones).
 template <bool FULL>
-int launch_tiles(qb200_ctx *ctx, BandTask *d_tasks, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base,
-                 unsigned class_mask = 0xffu)
+int tile_prepare(qb200_ctx *ctx, BandTask *d_tasks, const int *d_list, int begin, int n, bool first, bool want_lists = true)
 {
     if (n <= 0) return 0;
-    CK(ctx->d_tclass.reserve((size_t)kTileClasses * (size_t)n * 4));
+    if (want_lists) CK(ctx->d_tclass.reserve((size_t)kTileClasses * (size_t)n * 4));
     CK(ctx->d_tctl.reserve(sizeof(TileCtl)));
-    CK(ctx->d_punt.reserve((size_t)n * 4 + 16));
-    // tile-text pool: every task's text once more, aligned (the tasks of one launch are distinct (sub-)texts of the batch,
-    // forward and reverse pass of a Hirschberg node at most; 80 bytes of rounding per task)
-    CK(ctx->d_ttext.reserve(2 * (size_t)ctx->raw_bytes + (size_t)n * 80 + 64));
-    CK(cudaMemsetAsync(ctx->d_tctl.p, 0, sizeof(TileCtl), ctx->stream));
-    k_tile_classes<FULL><<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_tclass.as<int>(), n, ctx->d_tctl.as<TileCtl>()->counts,
-                                                                  &ctx->d_tctl.as<TileCtl>()->tt_words);
-    k_tile_text<FULL><<<(int)(((i64)n * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_codes.as<unsigned char>(), ctx->d_ttext.as<u64>());
+    if (first) {
+        // tile-text pool: every task's text once more, aligned (the tasks of one phase are distinct (sub-)texts of the
+        // batch, forward and reverse pass of a Hirschberg node at most; 80 bytes of rounding per task)
+        CK(ctx->d_ttext.reserve(2 * (size_t)ctx->raw_bytes + (size_t)std::max<i64>(ctx->n_pairs, n) * 160 + 64));
+        CK(cudaMemsetAsync(ctx->d_tctl.p, 0, sizeof(TileCtl), ctx->stream));
+    } else CK(cudaMemsetAsync(ctx->d_tctl.p, 0, offsetof(TileCtl, punt_count), ctx->stream));
+    k_tile_classes<FULL><<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, want_lists ? ctx->d_tclass.as<int>() : nullptr, n,
+                                                                  ctx->d_tctl.as<TileCtl>()->counts, &ctx->d_tctl.as<TileCtl>()->tt_words);
+    if (ctx->max_n > 1024)
+        k_tile_text<FULL, 32><<<(int)(((i64)n * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_codes.as<unsigned char>(), ctx->d_ttext.as<u64>());
+    else
+        k_tile_text<FULL, 4><<<(int)(((i64)n * 4 + 255) / 256), 256, 0, ctx->stream>>>(d_tasks, d_list, begin, n, ctx->d_codes.as<unsigned char>(), ctx->d_ttext.as<u64>());
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += 2;
+    return 0;
+}
+
+// BandEd fill of tasks[list[begin .. begin+n)] by the tile kernels, one launch per band-height class in class_mask.
+// FULL: writes tile records (pool d_matrix, task.mat_off in 16-byte units) + live ranges; !FULL: score-only passes.
+// Tasks the kernels give up on: FULL -> BandOut.pos_v = kTilePunted; !FULL -> appended to d_punt (count in d_tctl).
+template <bool FULL>
+int launch_tiles(qb200_ctx *ctx, BandTask *d_tasks, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base,
+                 unsigned class_mask = 0xffu, bool first = true)
+{
+    if (n <= 0) return 0;
+    CK(ctx->d_punt.reserve((size_t)std::max<i64>(ctx->n_pairs, n) * 4 + 16));
+    { const int rc = tile_prepare<FULL>(ctx, d_tasks, d_list, begin, n, first); if (rc) return rc; }
     TilePools P;
     P.ttext = ctx->d_ttext.as<u64>();
     P.tasks = d_tasks; P.codes = ctx->d_codes.as<unsigned char>(); P.peq = peq_base; P.recs = ctx->d_matrix.as<TileRec>();
@@ -420,13 +439,15 @@ inline unsigned tile_class_bit(i64 B)
     return 1u << c;
 }
 
-int launch_tile_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base)
+// thread_fill: the records come from the thread fill, which never gives a leaf up (no BandOut marker to look at)
+int launch_tile_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n, i64 sub, const u64 *peq_base, bool thread_fill = false)
 {
     if (n <= 0) return 0;
     ctx->tile_walks = true;
+    CK(ctx->d_punt.reserve((size_t)std::max<i64>(ctx->n_pairs, n) * 4 + 16));
     k_traceback_tiles<<<(n + kTileTraceThreads - 1) / kTileTraceThreads, kTileTraceThreads, 0, ctx->stream>>>(
         ctx->d_leaves.as<BandTask>(), d_list, begin, n, sub, ctx->d_ttext.as<u64>(), ctx->raw(), peq_base, ctx->d_matrix.as<TileRec>(),
-        ctx->d_ranges.as<int2>(), ctx->d_bandout.as<BandOut>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>(), ctx->d_punt.as<int>(),
+        ctx->d_ranges.as<int2>(), thread_fill ? nullptr : ctx->d_bandout.as<BandOut>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>(), ctx->d_punt.as<int>(),
         &ctx->d_tctl.as<TileCtl>()->punt_count);
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
@@ -868,8 +889,10 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         CK(cudaMemcpyAsync(slow_pairs.data(), ctx->d_list_slow.p, (size_t)tot.slow * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    // thread-kernel groups
-    if (tot.t > 0) {
+    // thread-kernel leaves: with the tile path they write tile records like everybody else (qb_banded.cuh, REC) and need
+    // no interleaved 32-leaf groups; the full-matrix mode (QB200_TILES=0) keeps the groups
+    const bool trec = ctx->use_tiles;
+    if (tot.t > 0 && !trec) {
         plan.n_groups = (int)((tot.t + 31) / 32);
         CK(ctx->d_gsize.reserve((size_t)plan.n_groups * 8));
         CK(ctx->d_goff.reserve((size_t)(plan.n_groups + 1) * 8));
@@ -910,27 +933,39 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         size_t free_b = 0, total_b = 0;
         if ((size_t)need * 16 > ctx->d_matrix.cap) CK(cudaMemGetInfo(&free_b, &total_b));
         const i64 limit = (i64)(std::min<size_t>(ctx->matrix_limit, std::max(ctx->d_matrix.cap, (size_t)((free_b + ctx->d_matrix.cap) * 0.85))) / 16);
-        if (need <= limit) {
-            CK(ctx->d_matrix.reserve((size_t)need * 16));
-            const bool tiles = ctx->use_tiles && (plan.tile_mask & 0xffu);
-            const bool wide = !ctx->use_tiles || (plan.tile_mask >> 31);          // leaves for the full-matrix warp kernels
-            const int min_B = ctx->use_tiles ? kTileBandMax + 1 : 0;
+        const bool tiles = ctx->use_tiles && (plan.tile_mask & 0xffu);
+        const bool wide = !ctx->use_tiles || (plan.tile_mask >> 31);          // leaves for the full-matrix warp kernels
+        const int min_B = ctx->use_tiles ? kTileBandMax + 1 : 0;
+        BandTask *d_lv = ctx->d_leaves.as<BandTask>();
+        const u64 *d_pq = ctx->d_peq.as<u64>();
+        // fill + traceback of thread-class leaves [t0, t0+tn) and wider leaves [w0, w0+wn) whose traceback state sits in the pool
+        auto fill_and_trace = [&](int t0, int tn, int w0, int wn, i64 sub_t, i64 sub_w) -> int {
             {
                 Span sp(ctx, ST_FILL);
-                int rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), 0, (int)tot.t, 0);
-                if (!rc && tiles) rc = launch_tiles<true>(ctx, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, ctx->d_peq.as<u64>(), plan.tile_mask & 0xffu);
-                if (!rc && wide) rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, nullptr, min_B);
+                int rc = 0;
+                if (trec && tn > 0) rc = tile_prepare<true>(ctx, d_lv, ctx->d_list_t.as<int>(), t0, tn, true, false);
+                if (!rc) rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), t0, tn, sub_t, nullptr, trec);
+                if (!rc && tiles && wn > 0) rc = launch_tiles<true>(ctx, d_lv, ctx->d_list_w.as<int>(), w0, wn, sub_w, d_pq, plan.tile_mask & 0xffu, !(trec && tn > 0));
+                if (!rc && wide && wn > 0) rc = launch_banded<true>(ctx, 127u, d_lv, ctx->d_list_w.as<int>(), w0, wn, sub_w, nullptr, min_B);
                 if (rc) return rc;
             }
             {
                 Span sp(ctx, ST_TRACE);
-                int rc = launch_traceback(ctx, ctx->d_list_t.as<int>(), 0, (int)tot.t, 0, false);
-                if (!rc && tiles) rc = launch_tile_traceback(ctx, ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, ctx->d_peq.as<u64>());
-                if (!rc && wide) rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), 0, (int)tot.w, 0, true, min_B);
+                int rc = 0;
+                if (trec) rc = launch_tile_traceback(ctx, ctx->d_list_t.as<int>(), t0, tn, sub_t, d_pq, true);
+                else rc = launch_traceback(ctx, ctx->d_list_t.as<int>(), t0, tn, sub_t, false);
+                if (!rc && tiles) rc = launch_tile_traceback(ctx, ctx->d_list_w.as<int>(), w0, wn, sub_w, d_pq);
+                if (!rc && wide) rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), w0, wn, sub_w, true, min_B);
                 if (rc) return rc;
             }
+            if ((tiles && wn > 0) || (trec && tn > 0)) return rerun_punted_leaves(ctx, d_pq);
+            return 0;
+        };
+        if (need <= limit) {
+            CK(ctx->d_matrix.reserve((size_t)need * 16));
+            const int rc = fill_and_trace(0, (int)tot.t, 0, (int)tot.w, 0, 0);
+            if (rc) return rc;
             ctx->stats.matrix_bytes += need * 16;
-            if (tiles) { int rc = rerun_punted_leaves(ctx, ctx->d_peq.as<u64>()); if (rc) return rc; }
         } else {
             CK(ctx->d_matrix.reserve((size_t)limit * 16));
             int *d_idx = reinterpret_cast<int *>(ctx->d_counters.as<u64>() + 20);
@@ -950,35 +985,25 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
                 if (e != cudaSuccess) { (void)cudaGetLastError(); ctx->err = "out of device memory for a single traceback matrix"; return QB200_ERR_OOM; }
                 return 0;
             };
-            // warp-kernel leaves
-            const bool tiles = ctx->use_tiles && (plan.tile_mask & 0xffu);
-            const bool wide = !ctx->use_tiles || (plan.tile_mask >> 31);
-            const int min_B = ctx->use_tiles ? kTileBandMax + 1 : 0;
-            for (int s0 = 0; s0 < (int)tot.w;) {
-                k_chunk_end_leaves<<<1, 1, 0, ctx->stream>>>(ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), (int)tot.w, s0, limit, d_idx, d_off, d_ent, ctx->use_tiles ? 1 : 0);
-                CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 24, cudaMemcpyDeviceToHost, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-                const int s1 = *reinterpret_cast<int *>(ctx->h_pinned);
-                const i64 sub = *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
-                { const int rc = fit_chunk(*reinterpret_cast<i64 *>(ctx->h_pinned + 8)); if (rc) return rc; }
-                {
-                    Span sp(ctx, ST_FILL);
-                    int rc = 0;
-                    if (tiles) rc = launch_tiles<true>(ctx, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub, ctx->d_peq.as<u64>(), plan.tile_mask & 0xffu);
-                    if (!rc && wide) rc = launch_banded<true>(ctx, 127u, ctx->d_leaves.as<BandTask>(), ctx->d_list_w.as<int>(), s0, s1 - s0, sub, nullptr, min_B);
+            // leaves whose state is laid out leaf by leaf: the wider ones, and with tile records the thread-class ones too
+            for (int pass = 0; pass < 2; ++pass) {
+                const bool thr = pass == 1;
+                if (thr && !trec) break;
+                const int *lst = thr ? ctx->d_list_t.as<int>() : ctx->d_list_w.as<int>();
+                const int cnt = (int)(thr ? tot.t : tot.w);
+                for (int s0 = 0; s0 < cnt;) {
+                    k_chunk_end_leaves<<<1, 1, 0, ctx->stream>>>(d_lv, lst, cnt, s0, limit, d_idx, d_off, d_ent, ctx->use_tiles ? 1 : 0);
+                    CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 24, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    const int s1 = *reinterpret_cast<int *>(ctx->h_pinned);
+                    const i64 sub = *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
+                    { const int rc = fit_chunk(*reinterpret_cast<i64 *>(ctx->h_pinned + 8)); if (rc) return rc; }
+                    const int rc = thr ? fill_and_trace(s0, s1 - s0, 0, 0, sub, 0) : fill_and_trace(0, 0, s0, s1 - s0, 0, sub);
                     if (rc) return rc;
+                    s0 = s1;
                 }
-                {
-                    Span sp(ctx, ST_TRACE);
-                    int rc = 0;
-                    if (tiles) rc = launch_tile_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub, ctx->d_peq.as<u64>());
-                    if (!rc && wide) rc = launch_traceback(ctx, ctx->d_list_w.as<int>(), s0, s1 - s0, sub, true, min_B);
-                    if (rc) return rc;
-                }
-                if (tiles) { int rc = rerun_punted_leaves(ctx, ctx->d_peq.as<u64>()); if (rc) return rc; }
-                s0 = s1;
             }
-            // thread-kernel groups
+            // thread-kernel groups (full-matrix mode)
             for (int g0 = 0; g0 < plan.n_groups;) {
                 k_chunk_end_groups<<<1, 1, 0, ctx->stream>>>(ctx->d_goff.as<i64>(), ctx->d_gsize.as<i64>(), plan.n_groups, g0, limit, d_idx, d_ent);
                 CK(cudaMemcpyAsync(ctx->h_pinned, d_idx, 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -988,8 +1013,8 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
                 { const int rc = fit_chunk(*reinterpret_cast<i64 *>(ctx->h_pinned + 8)); if (rc) return rc; }
                 const i64 sub = tot.matw + *reinterpret_cast<i64 *>(ctx->h_pinned + 16);
                 const int q0 = g0 * 32, q1 = (int)std::min<i64>(tot.t, (i64)g1 * 32);
-                { Span sp(ctx, ST_FILL); int rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), q0, q1 - q0, sub); if (rc) return rc; }
-                { Span sp(ctx, ST_TRACE); int rc = launch_traceback(ctx, ctx->d_list_t.as<int>(), q0, q1 - q0, sub); if (rc) return rc; }
+                const int rc = fill_and_trace(q0, q1 - q0, 0, 0, sub, 0);
+                if (rc) return rc;
                 g0 = g1;
             }
             ctx->stats.matrix_bytes += need * 16;
@@ -1225,8 +1250,10 @@ int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
         else if (ctx->use_tiles && tile_band_ok(g.Bc)) { list_x.push_back((int)i); xmask |= tile_class_bit(g.Bc); }
         else list_w.push_back((int)i);
         t.range_off = rg; rg += t.n / 64 + 2;
-        t.scores_off = sc; if (g.Bc > ctx->thread_band_max) sc += (i64)((t.m + 63) / 64) + g.Bc + 2;
+        t.scores_off = sc; if (g.Bc > ctx->thread_band_max || ctx->use_tiles) sc += (i64)((t.m + 63) / 64) + g.Bc + 2;
     }
+    const bool trec = ctx->use_tiles;       // thread-class leaves write tile records too (qb_banded.cuh, REC)
+    CK(ctx->d_punt.reserve((size_t)std::max<i64>(ctx->n_pairs, (i64)nl) * 4 + 16));
     // chunk plans: (kind: 1 thread kernel, 0 warp kernel, 2 tile kernels; list begin, list end, entries)
     struct Chunk { int thr, q0, q1; i64 ent; };
     std::vector<Chunk> chunks;
@@ -1243,7 +1270,19 @@ int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
         chunks.push_back({2, (int)q0, (int)q1, ent});
         q0 = q1;
     }
-    for (size_t g0 = 0; g0 < list_t.size();) {                       // thread-kernel groups of 32
+    for (size_t q0 = 0; trec && q0 < list_t.size();) {              // thread-class leaves in tile-record mode
+        i64 ent = 0; size_t q1 = q0;
+        while (q1 < list_t.size()) {
+            BandTask &t = leaves[list_t[q1]];
+            const i64 e = 2 * (i64)((t.n + 63) / 64) * Bc[list_t[q1]];
+            if (q1 > q0 && ent + e > limit) break;
+            t.mat_off = ent; t.mat_cs = Bc[list_t[q1]]; t.mat_ws = 1;
+            ent += e; ++q1;
+        }
+        chunks.push_back({3, (int)q0, (int)q1, ent});
+        q0 = q1;
+    }
+    for (size_t g0 = 0; !trec && g0 < list_t.size();) {             // thread-kernel groups of 32 (full-matrix mode)
         i64 ent = 0; size_t q0 = g0;
         while (g0 < list_t.size()) {
             const size_t g1 = std::min(list_t.size(), g0 + 32);
@@ -1284,6 +1323,19 @@ int run_leaves_host(qb200_ctx *ctx, std::vector<BandTask> &leaves, i64 L0)
     CK(cudaMemsetAsync(ctx->d_scores.p, 0, (size_t)sc * 4 + 16, ctx->stream));
     for (const Chunk &c : chunks) {
         CK(ctx->d_matrix.reserve((size_t)c.ent * 16));
+        if (c.thr == 3) {
+            {
+                Span sp(ctx, ST_FILL);
+                int rc = tile_prepare<true>(ctx, ctx->d_leaves.as<BandTask>(), ctx->d_list_t.as<int>(), c.q0, c.q1 - c.q0, true, false);
+                if (!rc) rc = launch_thread_fill(ctx, ctx->d_list_t.as<int>(), c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>(), true);
+                if (rc) return rc;
+            }
+            { Span sp(ctx, ST_TRACE); int rc = launch_tile_traceback(ctx, ctx->d_list_t.as<int>(), c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>(), true); if (rc) return rc; }
+            ctx->stats.matrix_bytes += c.ent * 16;
+            int rc = rerun_punted_leaves(ctx, ctx->d_peq2.as<u64>());       // synchronises
+            if (rc) return rc;
+            continue;
+        }
         if (c.thr == 2) {
             { Span sp(ctx, ST_FILL); int rc = launch_tiles<true>(ctx, ctx->d_leaves.as<BandTask>(), d_list_x, c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>(), xmask); if (rc) return rc; }
             { Span sp(ctx, ST_TRACE); int rc = launch_tile_traceback(ctx, d_list_x, c.q0, c.q1 - c.q0, 0, ctx->d_peq2.as<u64>()); if (rc) return rc; }

@@ -92,6 +92,10 @@ k_plan(const PairRec *__restrict__ pairs, int n, PlanParams pp, const int *__res
                 // 2-bit ops (thread walk, tile walk) / u32 runs, worst case (warp walk)
                 it.ops = (thr || tile) ? (r.m + r.n + 15) / 16 : (r.m + r.n + 15) / 16 * 16;
                 it.rng = r.n / 64 + 2;
+                if (thr && pp.tiles) {                  // thread fill in tile-record mode: same records, same walk as the wider bands
+                    it.sc = (r.m + 63) / 64 + g.Bc + 2;            // (scores only if the exact kernels have to redo the leaf)
+                    it.matw = 2 * (i64)((r.n + 63) / 64) * g.Bc;
+                }
                 if (!thr) {
                     it.sc = (r.m + 63) / 64 + g.Bc + 2;
                     // traceback state in 16-byte units: one 32-byte record per tile, or the reference's whole matrix
@@ -132,8 +136,8 @@ k_build_leaves(const PairRec *__restrict__ pairs, int n, const unsigned char *__
         BandTask t;
         t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = 0; t.finish = r.n;
         t.cutoff = cutoff[i]; t.peq_off = r.peq_off; t.nbp = r.nbp; t.pair = i;
-        t.mat_off = o.matw; t.mat_cs = 0; t.mat_ws = 1;
-        if (c == CLS_W) { const BandGeom g = band_geometry(r.m, r.n, t.cutoff); t.mat_cs = (int)g.Bc; }
+        t.mat_off = o.matw; t.mat_ws = 1;
+        { const BandGeom g = band_geometry(r.m, r.n, t.cutoff); t.mat_cs = (int)g.Bc; }     // band height (thread-kernel groups overwrite it)
         t.scores_off = o.sc; t.state_off = 0; t.ops_off = o.ops; t.range_off = o.rng;
         t.ops_cap = ((r.m + r.n + 15) / 16) * 16; t.slot = (int)o.leaf;
         leaves[o.leaf] = t;

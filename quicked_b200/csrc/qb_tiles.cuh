@@ -596,59 +596,93 @@ __global__ void __launch_bounds__(LANES + 32, LANES >= 128 ? 4 : LANES >= 64 ? 6
     }
 }
 
-// Task ids of `list` sorted into band-height classes (ring size 8 << c): out[c * cap + i], counts[c]; every task also
-// gets its place in the tile-text pool (tt_words: running total in u64 words).
+// Task ids of `list` sorted into band-height classes (ring size 8 << c): out[c * cap + i], counts[c] (skipped when out is
+// null: the thread fill needs no lists); every task also gets its place in the tile-text pool (tt_words: running total in
+// u64 words).  One atomic per warp for the pool, one per warp and class for the lists.
 template <bool FULL>
 __global__ void __launch_bounds__(256) k_tile_classes(BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n,
                                                       int *__restrict__ out, int cap, int *__restrict__ counts,
                                                       unsigned long long *__restrict__ tt_words)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int ti = list ? list[begin + i] : begin + i;
-    BandTask &t = tasks[ti];
-    const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
-    const int rb = tile_ring_for(FULL ? g.Bc : g.Bs);
-    if (rb > kTileMaxRing) return;                       // taller bands: the shared-memory sweep kernel (qb_banded.cuh)
-    int c = 0;
-    while ((8 << c) < rb) ++c;
-    out[(size_t)c * cap + atomicAdd(&counts[c], 1)] = ti;
-    const int ncols = FULL ? t.n : t.finish;
-    t.tt_off = (i64)atomicAdd(tt_words, (unsigned long long)((ncols + 63) / 64 * 8 + 1));   // +1: the prefetch past the last tile
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    int ti = -1, c = -1;
+    unsigned words = 0;
+    if (i < n) {
+        ti = list ? list[begin + i] : begin + i;
+        const BandTask &t = tasks[ti];
+        const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
+        const int rb = tile_ring_for(FULL ? g.Bc : g.Bs);
+        if (rb <= kTileMaxRing) {                        // taller bands: the shared-memory sweep kernel (qb_banded.cuh)
+            c = 0;
+            while ((8 << c) < rb) ++c;
+            const int ncols = FULL ? t.n : t.finish;
+            words = (unsigned)((ncols + 63) / 64 * 8 + 1);   // +1: the odd-character flag word
+        }
+    }
+    // text pool: warp-wide exclusive scan of the word counts, one atomic for the warp
+    unsigned incl = words;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += y; }
+    const unsigned total = __shfl_sync(kFull, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(tt_words, (unsigned long long)total);
+    base = __shfl_sync(kFull, base, 0);
+    if (c >= 0) tasks[ti].tt_off = (i64)(base + incl - words);
+    if (!out) return;
+    // class lists: lanes of the same class share one atomic
+#pragma unroll 1
+    for (int cc = 0; cc < 8; ++cc) {
+        const unsigned m = __ballot_sync(kFull, c == cc);
+        if (!m) continue;
+        int pos = 0;
+        if (lane == __ffs(m) - 1) pos = atomicAdd(&counts[cc], __popc(m));
+        pos = __shfl_sync(kFull, pos, __ffs(m) - 1);
+        if (c == cc) out[(size_t)cc * cap + pos + __popc(m & ((1u << lane) - 1u))] = ti;
+    }
 }
 
 // Tile-text pool: the text codes of a task, masked to the 3 code bits, in COLUMN order (a reversed pass reads its text
 // backwards), 8 columns per u64 and 8-byte aligned, so a tile's 64 codes are eight aligned loads with no realignment
-// in the fill's inner loop.  One warp per task; columns past the pass (ncols..64*ceil) are code 4.
-template <bool FULL>
+// in the fill's inner loop.  G lanes per task (32 for long texts, 4 for short reads); columns past the pass
+// (ncols..64*ceil) are code 4.
+template <bool FULL, int G>
 __global__ void __launch_bounds__(256) k_tile_text(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n,
                                                    const unsigned char *__restrict__ codes, u64 *__restrict__ ttext)
 {
-    const int wi = (int)(((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (wi >= n) return;
-    const BandTask &t = tasks[list ? list[begin + wi] : begin + wi];
-    const BandGeom g = band_geometry(t.m, t.n, t.cutoff);
-    if (tile_ring_for(FULL ? g.Bc : g.Bs) > kTileMaxRing) return;
-    const int ncols = FULL ? t.n : t.finish;
-    const int nw = (ncols + 63) / 64 * 8;
-    const unsigned char *src = codes + t.t_off;
-    u64 *dst = ttext + t.tt_off;
+    const i64 gt = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const int wi = (int)(gt / G), gl = (int)(gt % G);
+    const bool live = wi < n;
+    const BandTask *t = live ? &tasks[list ? list[begin + wi] : begin + wi] : nullptr;
+    bool ok = live;
+    if (live) {
+        const BandGeom g = band_geometry(t->m, t->n, t->cutoff);
+        ok = tile_ring_for(FULL ? g.Bc : g.Bs) <= kTileMaxRing;
+    }
     u32 odd = 0;
-    for (int w = lane; w < nw; w += 32) {
-        u64 v = 0;
+    int nw = 0;
+    u64 *dst = nullptr;
+    if (ok) {
+        const int ncols = FULL ? t->n : t->finish;
+        nw = (ncols + 63) / 64 * 8;
+        const unsigned char *src = codes + t->t_off;
+        dst = ttext + t->tt_off;
+        for (int w = gl; w < nw; w += G) {
+            u64 v = 0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int col = 8 * w + b;
-            const unsigned raw = col < ncols ? (unsigned)src[t.rev ? t.n - 1 - col : col] : 4u;
-            odd |= raw & kCodeOdd;
-            v |= (u64)(raw & 7u) << (8 * b);
+            for (int b = 0; b < 8; ++b) {
+                const int col = 8 * w + b;
+                const unsigned raw = col < ncols ? (unsigned)src[t->rev ? t->n - 1 - col : col] : 4u;
+                odd |= raw & kCodeOdd;
+                v |= (u64)(raw & 7u) << (8 * b);
+            }
+            dst[w] = v;
         }
-        dst[w] = v;
     }
     // last word of the task's slot: does the text hold a character outside "ACGTN"? (the tile traceback then compares
     // raw bytes on diagonal steps, reference bpm_banded.c:1012)
-    odd = __ballot_sync(kFull, odd != 0);
-    if (lane == 0) dst[nw] = odd ? 1ull : 0ull;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) odd |= __shfl_xor_sync(kFull, odd, o);
+    if (ok && gl == 0) dst[nw] = odd ? 1ull : 0ull;
 }
 
 }  // namespace qb

@@ -151,7 +151,7 @@ k_traceback_tiles(const BandTask *__restrict__ tasks, const int *__restrict__ li
     if (tile_ring_for(band_geometry(tk.m, tk.n, tk.cutoff).Bc) > kTileMaxRing) return;   // full-matrix leaf (warp kernels)
     LeafOut o;
     int rc = 3;
-    if (fill_out[tk.slot].pos_v != kTilePunted)
+    if (!fill_out || fill_out[tk.slot].pos_v != kTilePunted)
         rc = tile_traceback(tk, recs + (tk.mat_off - rec_sub) / 2, range_pool + tk.range_off, ttext, raw, peq, ops_pool + tk.ops_off,
                             s_planes + threadIdx.x, kTileTraceThreads, s_eq + threadIdx.x, kTileTraceThreads, o);
     if (rc) { punt_list[atomicAdd(punt_count, 1)] = ti; return; }

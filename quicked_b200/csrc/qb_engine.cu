@@ -445,6 +445,8 @@ int launch_tile_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n, i
     if (n <= 0) return 0;
     ctx->tile_walks = true;
     CK(ctx->d_punt.reserve((size_t)std::max<i64>(ctx->n_pairs, n) * 4 + 16));
+    static bool carve_set = false;
+    if (!carve_set) { cudaFuncSetAttribute(k_traceback_tiles, cudaFuncAttributePreferredSharedMemoryCarveout, 100); carve_set = true; }
     k_traceback_tiles<<<(n + kTileTraceThreads - 1) / kTileTraceThreads, kTileTraceThreads, 0, ctx->stream>>>(
         ctx->d_leaves.as<BandTask>(), d_list, begin, n, sub, ctx->d_ttext.as<u64>(), ctx->raw(), peq_base, ctx->d_matrix.as<TileRec>(),
         ctx->d_ranges.as<int2>(), thread_fill ? nullptr : ctx->d_bandout.as<BandOut>(), ctx->d_ops.as<u32>(), ctx->d_leafout.as<LeafOut>(), ctx->d_punt.as<int>(),
@@ -1038,10 +1040,17 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
         if (want_cigar) {
+            // pairs of >= kLongOps op slots (and multi-leaf pairs) get a warp each for the text passes
+            const bool long_pairs = !getenv("QB200_TEXT_THREAD") && (ctx->multi_leaf_pairs || (i64)ctx->max_m + ctx->max_n >= kLongOps);
             if (ctx->multi_leaf_pairs || ctx->tile_walks) {
                 CK(ctx->d_textlen.reserve((size_t)n * 4));
                 k_cigar_text<false><<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leaves.as<BandTask>(),
-                    ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), ctx->d_textlen.as<int>(), nullptr, nullptr);
+                    ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), ctx->d_textlen.as<int>(), nullptr, nullptr, long_pairs ? 1 : 0);
+                if (long_pairs) {
+                    k_cigar_text_warp<false><<<(ni + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leaves.as<BandTask>(),
+                        ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), ctx->d_textlen.as<int>(), nullptr, nullptr);
+                    ctx->stats.kernel_launches++;
+                }
                 k_merge_text_len<<<nb256, 256, 0, ctx->stream>>>(ctx->d_textlen.as<int>(), ctx->d_textbytes.as<i64>(), ni);
                 CK(cudaGetLastError());
                 ctx->stats.kernel_launches += 2;
@@ -1061,7 +1070,12 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
             CK(cudaMemsetAsync(ctx->d_cigar.p, 0, (size_t)ctx->cigar_total, ctx->stream));
             if (n_leaves > 0) {
                 k_cigar_text<true><<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leaves.as<BandTask>(),
-                    ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), nullptr, ctx->d_cigoff.as<i64>(), ctx->d_cigar.as<char>());
+                    ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), nullptr, ctx->d_cigoff.as<i64>(), ctx->d_cigar.as<char>(), long_pairs ? 1 : 0);
+                if (long_pairs) {
+                    k_cigar_text_warp<true><<<(ni + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_pairleaves.as<PairLeaves>(), ni, ctx->d_leaves.as<BandTask>(),
+                        ctx->d_leafout.as<LeafOut>(), ctx->d_ops.as<u32>(), nullptr, ctx->d_cigoff.as<i64>(), ctx->d_cigar.as<char>());
+                    ctx->stats.kernel_launches++;
+                }
                 CK(cudaGetLastError());
                 ctx->stats.kernel_launches++;
             }

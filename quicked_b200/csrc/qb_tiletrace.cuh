@@ -29,6 +29,29 @@ namespace qb {
 constexpr int kTraceCols = 64;        // plane words per thread (one per tile column)
 constexpr int kTraceHalf = 8;         // rows kept on each side of the walk's diagonal
 
+// One column of the recompute: the Myers block update of qb_tiles.cuh without the carry-outs (the record holds the tile's
+// carry-ins, top bit first in wp / wm).
+#define QB_TRACE_STEP(EQ)                                                                                   \
+    {                                                                                                       \
+        const u64 xv_ = (EQ) | mv;                                                                          \
+        const u64 xh_ = (add_with_top_bit((EQ) & pv, pv, wm) ^ pv) | (EQ);                                   \
+        const u64 ph_ = mv | ~(xh_ | pv);                                                                   \
+        const u64 mh_ = pv & xh_;                                                                           \
+        const u32 phl_ = (u32)ph_, phh_ = (u32)(ph_ >> 32), mhl_ = (u32)mh_, mhh_ = (u32)(mh_ >> 32);       \
+        const u64 ph2_ = ((u64)fsl32(phl_, phh_, 1) << 32) | (u64)fsl32(wp, phl_, 1);                       \
+        const u64 mh2_ = ((u64)fsl32(mhl_, mhh_, 1) << 32) | (u64)fsl32(wm, mhl_, 1);                       \
+        wp <<= 1; wm <<= 1;                                                                                 \
+        pv = mh2_ | ~(xv_ | ph2_);                                                                          \
+        mv = ph2_ & xv_;                                                                                    \
+    }
+
+// first row of the 16-row slice kept for tile column s: the walk's diagonal - kTraceHalf, clamped into the block
+QB_HD int trace_slice_lo(int lo0, int s)
+{
+    const int lo = lo0 + s;
+    return lo < 0 ? 0 : (lo > 48 ? 48 : lo);
+}
+
 // planes[s * ps]: decision planes of tile column s; eq[c * eqs]: the block's match masks; ttext: the task's aligned text
 // codes (tile-text pool, 8 per u64; its last word flags a text with characters outside "ACGTN").
 QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ranges, const u64 *ttext,
@@ -42,7 +65,7 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
     const u64 *tt = ttext + tk.tt_off;
     const bool text_odd = tt[(tk.n + 63) / 64 * 8] != 0;
     const unsigned char *praw = raw + tk.p_off, *traw = raw + tk.t_off;
-    LeanWriter w; w.init(ops, tk.ops_cap);
+    ShiftWriter w; w.init(ops, tk.ops_cap);
     int h = tk.n - 1, v = tk.m - 1;
     int eq_block = -1;
     u64 rowodd = 0;
@@ -57,71 +80,69 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
             // word j-1 there, which the reference only wrote from the new `first` on
             if (kb + 1 > nshift || j - 1 < ranges[kb + 1].x) return 2;
         }
+        // the tile's record and text first: one round trip for everything the recompute reads
+        const TileRec rec = recs[(i64)kb * B + j];
+        const u64 *tw = tt + 8 * (i64)kb;
+        u64 cw = tw[0];
         if (b != eq_block) {
 #pragma unroll
             for (int c = 0; c < kAlpha; ++c) eq[c * eqs] = pq[(i64)b * kPeqStride + c];
             rowodd = pq[(i64)b * kPeqStride + kAlpha];
             eq_block = b;
         }
-        // ---- recompute columns 0..s0 of tile (j, kb) ----
-        const TileRec rec = recs[(i64)kb * B + j];
+        // ---- recompute tile (j, kb) ----
         u64 pv = rec.pv0, mv = rec.mv0;
         const int lo0 = r0 - s0 - kTraceHalf;                        // lowest slice row at column 0 (may be negative)
-        // the walk stays within kTraceHalf rows of its diagonal and above row 0: it cannot reach columns below s_need
-        const int s_need = s0 - r0 - kTraceHalf;
-        const u64 *tw = tt + 8 * (i64)kb;
-        // eight columns per iteration (a tile has them: columns past s0 are computed for nothing, at most seven)
+        // ALL 64 columns, every column with its planes, whatever s0 is: the lanes of a warp walk different leaves, and a
+        // trip count or a "planes needed?" test that depends on the leaf makes them take turns (measured: 15 of 32 lanes
+        // active on average with both, and the kernel is bound by warp instructions on the integer pipe).  Columns past s0
+        // cost nothing extra that way; past the text they hold code 4 (k_tile_text) and are never read by the walk.
 #pragma unroll 1
-        for (int s8 = 0; s8 <= s0; s8 += 8) {
-            u64 cw = tw[s8 >> 3];
+        for (int s8 = 0; s8 < 64; s8 += 8) {
+            const u64 cnext = tw[(s8 >> 3) + 1];                     // the next group's codes (the pool has a word past every tile)
             u32 wp = (s8 < 32 ? rec.cin.p0 : rec.cin.p1) << (s8 & 31), wm = (s8 < 32 ? rec.cin.m0 : rec.cin.m1) << (s8 & 31);
-            const bool want = s8 + 7 >= s_need;
+            u32 *pl = planes + s8 * ps;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int s = s8 + i;
                 const u64 e = eq[(unsigned)(cw & 7u) * eqs];
                 cw >>= 8;
                 const u64 mv_old = mv;
-                {   // Myers block update without carry-outs (the record holds the tile's carry-ins, top bit first)
-                    const u64 xv = e | mv;
-                    const u64 eqh = e | (u64)(wm >> 31);
-                    const u64 xh = (((eqh & pv) + pv) ^ pv) | eqh;
-                    u64 ph = mv | ~(xh | pv);
-                    u64 mh = pv & xh;
-                    ph = (ph << 1) | (u64)(wp >> 31);
-                    mh = (mh << 1) | (u64)(wm >> 31);
-                    wp <<= 1; wm <<= 1;
-                    pv = mh | ~(xv | ph);
-                    mv = ph & xv;
-                }
-                if (want) {
-                    const u64 pa = pv | ~(mv_old | e), pb = ~pv & (mv_old | ~e);
-                    const int lo = lo0 + s;
-                    u32 sa, sb;
-                    if (lo >= 0) { sa = lo < 64 ? (u32)(pa >> lo) : 0u; sb = lo < 64 ? (u32)(pb >> lo) : 0u; }
-                    else { sa = -lo < 64 ? (u32)(pa << -lo) : 0u; sb = -lo < 64 ? (u32)(pb << -lo) : 0u; }
-                    planes[s * ps] = (sa & 0xffffu) | (sb << 16);
-                }
+                QB_TRACE_STEP(e);
+                const u64 pa = pv | ~(mv_old | e), pb = ~pv & (mv_old | ~e);
+                const int lo = trace_slice_lo(lo0, s8 + i);
+                const u32 sa = (u32)(pa >> lo), sb = (u32)(pb >> lo);
+#ifdef __CUDA_ARCH__
+                pl[i * ps] = __byte_perm(sa, sb, 0x5410);
+#else
+                pl[i * ps] = (sa & 0xffffu) | (sb << 16);
+#endif
             }
+            cw = cnext;
         }
         // ---- walk inside the tile ----
-        int r = r0, s = s0;
-        for (;;) {
-            if (r < 0 || s < 0) break;                               // left the tile through its top / left edge
-            const int q = (r - r0) + (s0 - s) + kTraceHalf;
-            if (q < 0 || q > 15) break;                              // drifted out of the slice: recompute around (r, s)
-            const u32 wd = planes[s * ps];
-            const u32 a = (wd >> q) & 1u, bb = (wd >> (16 + q)) & 1u;
-            int op;
-            if (a != bb) op = a ? OP_D : OP_I;
-            else {
-                op = a ? OP_X : OP_M;
-                if (text_odd || ((rowodd >> r) & 1ull))               // odd character: raw bytes decide (bpm_banded.c:1012)
-                    op = (traw[64 * kb + s] == praw[64 * b + r]) ? OP_M : OP_X;
+        int r = r0, s = s0, q = kTraceHalf;                          // q: row - (diagonal - kTraceHalf), the unclamped slice index
+        if (!(text_odd || rowodd != 0)) {
+            // until the walk leaves the tile (top / left edge) or drifts out of the slice
+            while ((r | s) >= 0 && (unsigned)q <= 15u) {
+                const u32 t2 = (planes[s * ps] >> (r - trace_slice_lo(lo0, s))) & 0x10001u;
+                const u32 a = t2 & 1u, bb = t2 >> 16;
+                w.emit((int)(((a ^ bb) << 1) | a));                  // (1,0) D = 3, (0,1) I = 2, (1,1) X = 1, (0,0) M = 0
+                q += (int)bb - (int)a;
+                r -= (int)(1u - (bb & ~a));                          // all but I consume a pattern row
+                s -= (int)(1u - (a & ~bb));                          // all but D consume a text column
             }
-            w.emit(op);
-            r -= (op != OP_I) ? 1 : 0;
-            s -= (op != OP_D) ? 1 : 0;
+        } else {
+            while ((r | s) >= 0 && (unsigned)q <= 15u) {
+                const u32 t2 = (planes[s * ps] >> (r - trace_slice_lo(lo0, s))) & 0x10001u;
+                const u32 a = t2 & 1u, bb = t2 >> 16;
+                int op = (int)(((a ^ bb) << 1) | a);
+                if (a == bb && (text_odd || ((rowodd >> r) & 1ull)))  // odd character: raw bytes decide (bpm_banded.c:1012)
+                    op = (traw[64 * kb + s] == praw[64 * b + r]) ? OP_M : OP_X;
+                w.emit(op);
+                q += (int)bb - (int)a;
+                r -= (op != OP_I) ? 1 : 0;
+                s -= (op != OP_D) ? 1 : 0;
+            }
         }
         v = 64 * b + r;
         h = 64 * kb + s;
@@ -135,7 +156,9 @@ QB_HD int tile_traceback(const BandTask &tk, const TileRec *recs, const int2 *ra
 
 #ifdef __CUDACC__
 // One leaf per thread; leaves that punt are appended to punt_list for the exact kernels.
-constexpr int kTileTraceThreads = 128;
+// 64 threads: 19 KB of shared memory per CTA, eleven CTAs = 704 leaves per SM.  100 k leaves (BASELINE configs[2]) then are
+// ONE wave; with 128-thread CTAs (five per SM) 42 of 782 CTAs formed a second wave that doubled the kernel's time.
+constexpr int kTileTraceThreads = 64;
 __global__ void __launch_bounds__(kTileTraceThreads)
 k_traceback_tiles(const BandTask *__restrict__ tasks, const int *__restrict__ list, int begin, int n_tasks, i64 rec_sub,
                   const u64 *__restrict__ ttext, const unsigned char *__restrict__ raw, const u64 *__restrict__ peq,

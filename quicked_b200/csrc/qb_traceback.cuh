@@ -57,6 +57,35 @@ struct LeanWriter {
     __host__ __device__ __forceinline__ void finish() { if (pos & 15) words[pos >> 4] = acc; }
 };
 
+// LeanWriter as a shift register: an op costs one multiply-add (acc = 4 * acc + op: the first op of a word ends up in its
+// top field), the word leaves when its 16 ops are in, and the edit cost is counted per stored word (non-zero 2-bit
+// fields), not per op.
+struct ShiftWriter {
+    u32 *words;
+    int pos, cost;
+    u32 acc;
+    __host__ __device__ __forceinline__ static int nonzero_fields(u32 a)
+    {
+        const u32 x = (a | (a >> 1)) & 0x55555555u;
+#ifdef __CUDA_ARCH__
+        return __popc(x);
+#else
+        return __builtin_popcount(x);
+#endif
+    }
+    __host__ __device__ __forceinline__ void init(u32 *w, int cap) { words = w; pos = cap; acc = 0; cost = 0; }
+    __host__ __device__ __forceinline__ void emit(int op)
+    {
+        acc = acc * 4u + (u32)op;
+        --pos;
+        if ((pos & 15) == 0) { words[pos >> 4] = acc; cost += nonzero_fields(acc); acc = 0; }
+    }
+    __host__ __device__ __forceinline__ void finish()
+    {
+        if (pos & 15) { words[pos >> 4] = acc << (2 * (pos & 15)); cost += nonzero_fields(acc); }
+    }
+};
+
 // Was band word `w` of stored column `c` ever written by the fill?  Column c (state after c text columns) was written
 // with the live range of column block (c-1)/64; a column with c%64==0 is stored after the shift, i.e. with the next
 // block's first and the previous block's last (bpm_banded.c:279-287).  Never-written cells read as 0, which is what
@@ -367,7 +396,19 @@ struct TextSink {
         put(0ull, 1); --total;
         for (int k = skip; k < n; ++k) base[k] = (char)(acc >> (8 * k));
     }
+    __device__ __forceinline__ void finish_raw()            // the partial word only (a piece inside a longer text)
+    {
+        for (int k = skip; k < n; ++k) base[k] = (char)(acc >> (8 * k));
+    }
 };
+
+// Pairs whose text the warp kernel (k_cigar_text_warp) writes: several leaves (Hirschberg pairs are long by
+// construction) or one leaf of >= kLongOps op slots.
+constexpr int kLongOps = 4096;
+__device__ __forceinline__ bool pair_is_long(const PairLeaves &p, const BandTask *__restrict__ leaves)
+{
+    return p.n_leaves > 1 || (p.n_leaves == 1 && leaves[p.first_leaf].ops_cap >= kLongOps);
+}
 
 // Pass over a pair's ops, merging runs across leaf boundaries.  WRITE=false: only measure (text bytes without NUL,
 // and the edit cost); WRITE=true: write the text at cigar + cigar_off[pair] and NUL-terminate.
@@ -375,11 +416,12 @@ template <bool WRITE>
 __global__ void __launch_bounds__(128)
 k_cigar_text(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask *__restrict__ leaves,
              const LeafOut *__restrict__ leaf_out, const u32 *__restrict__ ops_pool, int *__restrict__ text_len,
-             const i64 *__restrict__ cigar_off, char *__restrict__ cigar)
+             const i64 *__restrict__ cigar_off, char *__restrict__ cigar, int skip_long)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const PairLeaves p = pl[i];
+    if (skip_long && pair_is_long(p, leaves)) return;      // k_cigar_text_warp's
     if (!WRITE && (p.n_leaves < 1 || (p.n_leaves == 1 && leaf_out[p.first_leaf].text_len >= 0))) return;   // the walk already measured it
     if (WRITE && p.n_leaves == 0) return;        // empty string: the buffer is pre-zeroed
     TextSink sink;
@@ -432,6 +474,137 @@ k_cigar_text(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask *__r
     close_run();
     if (WRITE) sink.finish();
     else text_len[i] = out;
+}
+
+// The same pass with ONE WARP PER PAIR, for long pairs (pair_is_long): a 10 kbp pair has ~12 k ops, a 100 kbp pair
+// ~120 k, and one thread walking them alone is a chain of that length (3 ms per 100 k pairs of 10 kbp, 21 ms per 2 k
+// pairs of 100 kbp).  Here every lane takes one 16-op word of a 512-op batch, finds the run starts inside its word with
+// the XOR trick above, and CLOSES the runs that end in its word: the run's first op comes from a max-scan of the
+// lanes' last run starts (the open run of the previous batch / leaf rides along as a negative coordinate).  An
+// exclusive scan of the lanes' text bytes gives every lane its place in the output.
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+k_cigar_text_warp(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask *__restrict__ leaves,
+                  const LeafOut *__restrict__ leaf_out, const u32 *__restrict__ ops_pool, int *__restrict__ text_len,
+                  const i64 *__restrict__ cigar_off, char *__restrict__ cigar)
+{
+    __shared__ __align__(16) unsigned char s_stage[WRITE ? 4 : 1][WRITE ? 1056 : 16];   // <= 2 bytes per op of a 512-op batch + one long run
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_pairs) return;
+    const PairLeaves p = pl[i];
+    if (!pair_is_long(p, leaves)) return;
+    char *dst = WRITE ? cigar + cigar_off[i] : nullptr;
+    constexpr int NONE = -0x40000000;
+    int out = 0;                           // text bytes so far (warp-uniform)
+    int cur_op = -1, cur_len = 0;          // the open run (warp-uniform)
+    for (int l = 0; l < p.n_leaves; ++l) {
+        const BandTask &tk = leaves[p.first_leaf + l];
+        const LeafOut lo = leaf_out[p.first_leaf + l];
+        const u32 *words = ops_pool + tk.ops_off;
+        const int end = tk.ops_cap, pos0 = end - lo.n_ops;
+        if (lo.n_ops <= 0) continue;
+        if (lo.fmt == 1) {                                   // u32 runs (full-matrix warp traceback): rare, walked uniformly
+            for (int pos = pos0; pos < end; ++pos) {
+                const u32 r = words[pos];
+                const int op = (int)(r & 3u), len = (int)(r >> 2);
+                if (op == cur_op) { cur_len += len; continue; }
+                if (cur_op >= 0) {
+                    if (WRITE && lane == 0) { TextSink sk; sk.init(dst + out); sk.put_run(cur_len, cur_op); sk.finish_raw(); }
+                    out += dec_digits((unsigned)cur_len) + 1;
+                }
+                cur_op = op; cur_len = len;
+            }
+            continue;
+        }
+        const int wfirst = pos0 >> 4, wlast = (end - 1) >> 4;
+        for (int w0 = wfirst; w0 <= wlast; w0 += 32) {
+            const int widx = w0 + lane;
+            const bool have = widx <= wlast;
+            const u32 wv = have ? __ldg(words + widx) : 0u;
+            const int lo_k = (widx == wfirst) ? (pos0 & 15) : 0;
+            const int hi_k = have ? (widx == wlast ? ((end - 1) & 15) + 1 : 16) : 0;
+            // the op in front of this word's first op: the open run's op for the first word of the batch, else the
+            // previous lane's top op
+            const u32 up = __shfl_up_sync(kFull, wv >> 30, 1);
+            const int prev_op = (lane == 0) ? cur_op : (int)up;
+            u32 prevv = wv << 2;
+            prevv = (prevv & ~(3u << (2 * lo_k))) | ((u32)(prev_op & 3) << (2 * lo_k));
+            const u32 diff = wv ^ prevv;
+            u32 chg = (diff | (diff >> 1)) & 0x55555555u;
+            if (prev_op < 0) chg |= 1u << (2 * lo_k);
+            chg &= (hi_k == 16 ? 0xffffffffu : ((1u << (2 * hi_k)) - 1u)) & ~((1u << (2 * lo_k)) - 1u);
+            // coordinates: op k of lane's word sits at 16 * lane + k; the open run started at first - cur_len
+            const int first = (w0 == wfirst) ? (pos0 & 15) : 0;
+            const int open_start = (cur_op >= 0) ? first - cur_len : NONE;
+            const int ls = chg ? 16 * lane + ((31 - __clz((int)chg)) >> 1) : NONE;
+            int incl = ls;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl = max(incl, y); }
+            int prev = __shfl_up_sync(kFull, incl, 1);
+            if (lane == 0) prev = NONE;
+            prev = max(prev, open_start);
+            // pass 1: text bytes of the runs that end in this word
+            int bytes = 0;
+            {
+                int pv = prev; u32 c = chg;
+                while (c) {
+                    const int k = (__ffs((int)c) - 1) >> 1;
+                    c &= c - 1;
+                    const int st = 16 * lane + k;
+                    if (pv != NONE) bytes += dec_digits((unsigned)(st - pv)) + 1;
+                    pv = st;
+                }
+            }
+            int bi = bytes;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(kFull, bi, o); if (lane >= o) bi += y; }
+            const int total = __shfl_sync(kFull, bi, 31);
+            if (WRITE && total) {
+                // the batch's text is staged in shared memory and leaves as aligned 4-byte words (one byte store per
+                // character is store-transaction bound); stage[j] maps to the global byte (dst + out - mis) + j
+                unsigned char *stg = s_stage[threadIdx.x >> 5];
+                const int mis = (int)((unsigned long long)(dst + out) & 3ull);
+                if (bytes) {
+                    unsigned char *q = stg + mis + (bi - bytes);
+                    int pv = prev; u32 c = chg;
+                    while (c) {
+                        const int k = (__ffs((int)c) - 1) >> 1;
+                        c &= c - 1;
+                        const int st = 16 * lane + k;
+                        if (pv != NONE) {
+                            unsigned x = (unsigned)(st - pv);
+                            const int nd = dec_digits(x);
+                            for (int d = nd - 1; d >= 0; --d) { q[d] = (unsigned char)('0' + x % 10u); x /= 10u; }
+                            q[nd] = (unsigned char)"MXID"[k > lo_k ? (int)((wv >> (2 * (k - 1))) & 3u) : prev_op];
+                            q += nd + 1;
+                        }
+                        pv = st;
+                    }
+                }
+                __syncwarp();
+                char *g = dst + out - mis;
+                const int nb = mis + total;
+                for (int b0 = 4 * lane; b0 < nb; b0 += 128) {
+                    if (b0 >= mis && b0 + 4 <= nb) *reinterpret_cast<u32 *>(g + b0) = *reinterpret_cast<const u32 *>(stg + b0);
+                    else for (int k = max(b0, mis); k < min(b0 + 4, nb); ++k) g[k] = (char)stg[k];
+                }
+                __syncwarp();
+            }
+            out += total;
+            // the open run after this batch
+            const int nw = min(32, wlast - w0 + 1);
+            const int hi_last = (w0 + nw - 1 == wlast) ? ((end - 1) & 15) + 1 : 16;
+            const int last_start = max(__shfl_sync(kFull, incl, 31), open_start);
+            cur_op = (int)((__shfl_sync(kFull, wv, nw - 1) >> (2 * (hi_last - 1))) & 3u);
+            cur_len = 16 * (nw - 1) + hi_last - last_start;
+        }
+    }
+    if (cur_op >= 0) {
+        if (WRITE && lane == 0) { TextSink sk; sk.init(dst + out); sk.put_run(cur_len, cur_op); sk.finish_raw(); }
+        out += dec_digits((unsigned)cur_len) + 1;
+    }
+    if (!WRITE && lane == 0) text_len[i] = out;
 }
 
 }  // namespace qb

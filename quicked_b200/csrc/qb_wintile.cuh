@@ -63,7 +63,7 @@ k_windowed_tiles(const WinTask *__restrict__ tasks, int n_tasks, const unsigned 
         if (W > Wmax || (tk.sse && W == 2)) { WinOut wo; wo.score = 0; wo.hew = kWinPunted; outs[tk.slot] = wo; continue; }
         const u64 *pq = peq + tk.peq_off;
         const unsigned char *tc = codes + tk.t_off;
-        LeanWriter ow;
+        ShiftWriter ow;
         if (!SCORE_ONLY) ow.init(ops_pool + tk.ops_off, tk.ops_cap);
         int cv = tk.m - 1, ch = tk.n - 1, score = 0, hew = 0;
         const int hew_lim = (W - O) * 64 * tk.hew_threshold / 100;

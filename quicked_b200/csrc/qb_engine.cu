@@ -125,6 +125,7 @@ struct qb200_ctx {
     DevBuf d_fmat, d_franges, d_done;      // fused fast path: per-resident-warp matrix slots, live ranges, per-pair done flags
     i64 ops_words_fused = 0;               // op words of all pairs (fused-path region of the op pool)
     int max_n = 0, max_m = 0;
+    bool ws_compact_set[2] = {false, false};
     int ws_carve_set[2][2] = {{-1, -1}, {-1, -1}};   // shared-memory carve-out already requested for each WindowEd(S) kernel variant
     int sms = 0;                           // SM count of the device (queried once)
     DevBuf d_tclass, d_tctl, d_punt, d_gather, d_ttext, d_wintile;   // tile path: per-class task lists, counters, punted tasks
@@ -817,14 +818,23 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         // better that way than as a full wave plus a nearly empty one (100 k pairs: 10.7 vs 11.2 ms)
         if (n <= (i64)sms * 5 * kWsThreads * 11 / 10) ctas = 5;
         if (const char *e = getenv("QB200_WS_CTAS")) ctas = std::max(1, std::min(atoi(e), (int)kWsCtasPerSm));
-        const int blocks = (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms * ctas);   // persistent: one wave
-        CK(ctx->d_quad.reserve((size_t)blocks * kWsThreads * kWsQuadSlots * 8));
         // Batches with texts of >= 128 characters have full windows: the SLIM kernel keeps their quadrants in shared
         // memory (43.5 KB per CTA).  Shorter reads only ever run non-full windows, whose quadrant lives in the L2
         // scratch: there the 10 KB kernel with most of the SM left as L1 is the faster one (C1: 4.2 vs 5.6 ms per 4 M).
         const bool slim = ctx->max_n >= 128;
+        // COMPACT residency (704 pairs per SM, qb_windowed.cuh) when that turns two waves into one
+        const i64 cap = (i64)sms * ctas * kWsThreads, cap_c = (i64)sms * 2 * kWsCompactThreads;
+        bool compact = slim && n > cap && n <= cap_c;
+        if (const char *e = getenv("QB200_WS_COMPACT")) compact = slim && atoi(e) != 0;
+        const int T = compact ? kWsCompactThreads : kWsThreads;
+        const int blocks = (int)std::min<i64>((n + T - 1) / T, compact ? (i64)sms * 2 : (i64)sms * ctas);   // persistent: one wave
+        // the plain kernel: all pairs, or (after the COMPACT one) the pairs that one skipped
+        const int blocks_p = compact ? (int)std::min<i64>((n + kWsThreads - 1) / kWsThreads, (i64)sms) : blocks;
+        CK(ctx->d_quad.reserve((size_t)std::max<i64>((i64)blocks * T, (i64)blocks_p * kWsThreads) * kWsQuadSlots * 8));
         auto kern = prm.force_scalar ? (slim ? k_windowed21_score<false, true> : k_windowed21_score<false, false>)
                                      : (slim ? k_windowed21_score<true, true> : k_windowed21_score<true, false>);
+        auto kern_c = prm.force_scalar ? k_windowed21_score<false, true, true> : k_windowed21_score<true, true, true>;
+        const size_t smem = ws_smem_bytes(slim, kWsThreads, kAlpha), smem_c = ws_smem_bytes(true, kWsCompactThreads, 4);
         {   // carve out what the resident CTAs need (+1 KB per CTA of system use), the rest stays L1
             int carve = std::min(100, (ctas * (slim ? 45 : 11) * 100 + 227) / 228 + 1);
             if (const char *e = getenv("QB200_WS_CARVE")) carve = atoi(e);
@@ -832,10 +842,21 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
                 cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
                 ctx->ws_carve_set[prm.force_scalar ? 1 : 0][slim ? 1 : 0] = carve;
             }
+            if (compact && !ctx->ws_compact_set[prm.force_scalar ? 1 : 0]) {
+                CK(cudaFuncSetAttribute(kern_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+                cudaFuncSetAttribute(kern_c, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                ctx->ws_compact_set[prm.force_scalar ? 1 : 0] = true;
+            }
         }
-        kern<<<blocks, kWsThreads, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+        if (compact) {
+            kern_c<<<blocks, kWsCompactThreads, smem_c, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
+                ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(),
+                ctx->d_quad.as<u64>(), ctx->d_pairodd.as<unsigned char>(), 0);
+            ctx->stats.kernel_launches++;
+        }
+        kern<<<blocks_p, kWsThreads, smem, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(), ctx->raw(),
             ctx->d_peq.as<u64>(), (int)prm.hew_threshold[0], ctx->d_bound.as<int>(), ctx->d_hew.as<int>(), ctx->d_counters.as<u64>(),
-            ctx->d_quad.as<u64>(), ctx->d_pairodd.as<unsigned char>());
+            ctx->d_quad.as<u64>(), ctx->d_pairodd.as<unsigned char>(), compact ? 1 : 0);
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
     }

@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(256) k_make_peqjobs(const PairRec *__restrict_
 
 // One warp per table.  Each iteration covers one 64-row block: two coalesced 32-byte reads of codes, five ballots
 // each.  Rows >= m inside the last block match every code (reference bpm_banded.c:77-86); the two extra blocks are 0.
-// With job.flag >= 0 the warp also reports whether the pattern or the text holds a character outside "ACGTN" (the
-// WindowEd(S) kernel prices diagonal steps from the match masks only for pairs without any).
+// With job.flag >= 0 the warp also reports whether the pattern holds a character outside "ACGTN" or the text one outside
+// "ACGT" (the WindowEd(S) kernel prices diagonal steps from the match masks only for pairs without any, and its compact
+// variant keeps no match-mask row for code 4).
 __global__ void __launch_bounds__(256) k_build_peq(const PeqJob *__restrict__ jobs, int n_jobs,
                                                    const unsigned char *__restrict__ codes, u64 *__restrict__ peq,
                                                    unsigned char *__restrict__ odd_flags)
@@ -99,9 +100,9 @@ __global__ void __launch_bounds__(256) k_build_peq(const PeqJob *__restrict__ jo
         const unsigned long long t0 = (unsigned long long)(codes + job.t_off), t1 = t0 + (unsigned long long)job.n, a0 = t0 & ~3ull;
         u32 acc = 0;
         for (unsigned long long a = a0 + 4ull * lane; a < t1; a += 128) {
-            u32 msk = 0x08080808u;                                   // kCodeOdd of the bytes that belong to the text
+            u32 msk = 0x0c0c0c0cu;                                   // kCodeOdd or code 4 (not A, C, G, T) in the bytes that belong to the text
             if (a < t0) msk <<= 8 * (unsigned)(t0 - a);
-            if (a + 4 > t1) msk &= 0x08080808u >> (8 * (unsigned)(a + 4 - t1));
+            if (a + 4 > t1) msk &= 0x0c0c0c0cu >> (8 * (unsigned)(a + 4 - t1));
             acc |= *reinterpret_cast<const u32 *>(a) & msk;
         }
         any_odd |= __ballot_sync(kFull, acc != 0);
@@ -163,9 +164,9 @@ __global__ void __launch_bounds__(128) k_build_peq_pairs(const PairRec *__restri
     // odd characters of the text: aligned 8-byte words, bytes outside the text masked off
     const unsigned long long t0 = (unsigned long long)(codes + r.t_off), t1 = t0 + (unsigned long long)r.n;
     for (unsigned long long a = t0 & ~7ull; a < t1; a += 8) {
-        u64 msk = 0x0808080808080808ull;
+        u64 msk = 0x0c0c0c0c0c0c0c0cull;                              // kCodeOdd, or code 4: a text character that is not A, C, G, T
         if (a < t0) msk <<= 8 * (unsigned)(t0 - a);
-        if (a + 8 > t1) msk &= 0x0808080808080808ull >> (8 * (unsigned)(a + 8 - t1));
+        if (a + 8 > t1) msk &= 0x0c0c0c0c0c0c0c0cull >> (8 * (unsigned)(a + 8 - t1));
         any_odd |= __ldg(reinterpret_cast<const u64 *>(a)) & msk;
     }
     odd_flags[i] = any_odd ? 1 : 0;

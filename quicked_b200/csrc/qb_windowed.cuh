@@ -43,12 +43,11 @@ __device__ __forceinline__ u32 slim_entry(u64 pv, u64 mv_prev, u64 eq, int s)
 // of all but the last one or two windows of a pair.  STORE 0: nothing is kept (columns 0..63), 1: Pv/Mv of word 1 go
 // to the L2/HBM scratch, 2: the walk decisions go to shared memory (SLIM).  w0/w1: the eight columns' code bytes.
 // The body is kept this small on purpose: the kernel's hot loop has to stay inside the 32 KB instruction cache.
-template <bool SSE, int STORE>
+template <bool SSE, int STORE, int T = kWsThreads, int NC = kAlpha>
 __device__ __forceinline__ void ws_full_group8(u32 w0, u32 w1, int c0, u32 top_in, const u64 *weq,
                                                u64 &pv0, u64 &mv0, u64 &pv1, u64 &mv1, u64 &pv1_prev, u64 &mv1_prev,
                                                u64 *qpv, u64 *qmv, i64 nthr, u32 *sq)
 {
-    constexpr int T = kWsThreads;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int c = c0 + k;
@@ -58,7 +57,7 @@ __device__ __forceinline__ void ws_full_group8(u32 w0, u32 w1, int c0, u32 top_i
         u32 hp, hm, o1, o2;
         myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
         if (SSE && c == 127) { pv1_prev = pv1; mv1_prev = mv1; }
-        const u64 eq1 = weq[(kAlpha + code) * T], mv1_before = mv1;
+        const u64 eq1 = weq[(NC + code) * T], mv1_before = mv1;
         myers_step(eq1, pv1, mv1, hp, hm, o1, o2);
         if (STORE == 2) sq[(c - 63) * T] = slim_entry(pv1, mv1_before, eq1, c - 63);
         if (STORE == 1) {
@@ -77,13 +76,17 @@ __device__ __forceinline__ void ws_full_group8(u32 w0, u32 w1, int c0, u32 top_i
 // of the other (about 1 window in 10^4 at 10 % error).  If it does leave the slice, the window is simply recomputed
 // with the full 64-row quadrant in the L2/HBM scratch (the path non-full windows always take), so the result never
 // depends on the slice width.  The walk then touches global memory only for characters outside "ACGTN".
-template <bool SSE, bool SLIM>
+//
+// T: threads per CTA (the stride of the shared-memory slots).  NC: match-mask rows kept per window word — kAlpha, or 4
+// for pairs whose TEXT holds only A, C, G, T (k_build_peq_pairs flags the others): their columns never look the code-4
+// row up, except the SSE look-ahead past the end of the text, which takes it from a register.  64 + 260 bytes of shared
+// memory per pair instead of 80 + 260 is what lets 704 pairs share an SM (k_windowed21_score, COMPACT).
+template <bool SSE, bool SLIM, int T = kWsThreads, int NC = kAlpha>
 __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char *__restrict__ codes,
                                           const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, u64 *weq,
                                           u64 *qpv, u64 *qmv, i64 nthr, u32 *sq, bool slim_ok, int hew_lim, int &score_out,
                                           int &hew_out, u64 &ws)
 {
-    constexpr int T = kWsThreads;
         int score = 0, hew = 0;
         int cv = pr.m - 1, ch = pr.n - 1;                    // corner (pos_v,pos_h), bpm_windowed.c:148-149
         if (pr.m > 0 && pr.n > 0) {
@@ -99,6 +102,7 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                 const int cs = h_stop - h0;                  // first stored column index the walk can touch
                 const unsigned r0 = (unsigned)(v_stop - v0); // first row of the 64-row slice, 0..64
                 // ---- match masks re-aligned to the window origin (bpm_windowed.c:237-244) ----
+                u64 eq0_code4;                               // word 0's row of code 4 (only read when NC < kAlpha)
                 {
                     const unsigned sh = v0 & 63;
                     const int blk0 = v0 >> 6;
@@ -116,10 +120,11 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                         c2[0] = q6.x; c2[1] = q6.y; c2[2] = q7.x; c2[3] = q7.y; c2[4] = q8.x;
                     }
 #pragma unroll
-                    for (int c = 0; c < kAlpha; ++c) {
+                    for (int c = 0; c < NC; ++c) {
                         weq[c * T] = funnel_r(a[c], b[c], sh);
-                        weq[(kAlpha + c) * T] = (words == 2) ? funnel_r(b[c], c2[c], sh) : 0ull;
+                        weq[(NC + c) * T] = (words == 2) ? funnel_r(b[c], c2[c], sh) : 0ull;
                     }
+                    eq0_code4 = funnel_r(a[kAlpha - 1], b[kAlpha - 1], sh);
                 }
                 u64 pv0 = (h0 == 0) ? ~0ull : 0ull, pv1 = pv0, mv0 = 0, mv1 = 0;   // :225-229
                 const u32 top_in = (v0 == 0);                                      // :247-252
@@ -147,12 +152,12 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                         }
                         const u32 w0 = (q & 1) ? r.z : r.x, w1 = (q & 1) ? r.w : r.y;
                         if (q < 8) {
-                            ws_full_group8<SSE, 0>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
+                            ws_full_group8<SSE, 0, T, NC>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
                             if (q == 7 && !slim) { qpv[0] = pv1; qmv[0] = mv1; }     // stored column 0: the state after window column 63
                         } else if (slim) {
-                            ws_full_group8<SSE, 2>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
+                            ws_full_group8<SSE, 2, T, NC>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
                         } else {
-                            ws_full_group8<SSE, 1>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
+                            ws_full_group8<SSE, 1, T, NC>(w0, w1, q * 8, top_in, weq, pv0, mv0, pv1, mv1, pv1_prev, mv1_prev, qpv, qmv, nthr, sq);
                         }
                     }
                     code_last = r.w >> 24;
@@ -180,7 +185,7 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                                 if (words == 2) {
                                     if (SSE && c == cols - 1) { pv1_prev = pv1; mv1_prev = mv1; }
                                     if (SSE && cols == 1) { hp = 0; hm = 0; }              // uninitialised carry in the reference
-                                    myers_step(weq[(kAlpha + code) * T], pv1, mv1, hp, hm, o1, o2);
+                                    myers_step(weq[(NC + code) * T], pv1, mv1, hp, hm, o1, o2);
                                 }
                                 if (c + 1 >= cs) {
                                     const i64 s = (i64)(c + 1 - cs) * nthr;
@@ -197,9 +202,9 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                     const int code_la = (ti < pr.n) ? (int)(tc[ti] & 7) : 4;
                     u64 lpv = pv0, lmv = mv0;
                     u32 hpL, hmL, o1, o2;
-                    myers_step(weq[code_la * T], lpv, lmv, 1u, 0u, hpL, hmL);
+                    myers_step((NC < kAlpha && code_la >= NC) ? eq0_code4 : weq[code_la * T], lpv, lmv, 1u, 0u, hpL, hmL);
                     pv1 = pv1_prev; mv1 = mv1_prev;
-                    const u64 eq1 = weq[(kAlpha + (code_last & 7u)) * T];
+                    const u64 eq1 = weq[(NC + (code_last & 7u)) * T];
                     myers_step(eq1, pv1, mv1, hpL, hmL, o1, o2);
                     if (slim) sq[64 * T] = slim_entry(pv1, mv1_prev, eq1, 64);
                     else {
@@ -263,16 +268,26 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
         score_out = score; hew_out = hew;
 }
 
-template <bool SSE, bool SLIM>
-__global__ void __launch_bounds__(kWsThreads, kWsCtasPerSm)
+// COMPACT (SLIM only): CTAs of kWsCompactThreads threads, two per SM, four match-mask rows per word — 704 pairs per SM
+// instead of 640.  A pair is a chain of ~n/64 windows, so a batch that overflows the resident threads by a few pairs
+// pays a whole second chain for them: 100 k pairs of 10 kbp (BASELINE configs[2]) are 94 720 + 5 280 with 128-thread
+// CTAs (10.7 ms) and one wave here.  Pairs flagged by the table builder (a character outside "ACGT" in the text, or
+// outside "ACGTN" anywhere) are skipped by the COMPACT kernel and done by a launch of the plain one with only_flagged.
+constexpr int kWsCompactThreads = 352;
+__host__ __device__ constexpr size_t ws_smem_bytes(bool slim, int T, int NC) { return (size_t)T * (2 * NC * 8 + (slim ? 65 * 4 : 0)) + (slim ? 0 : 16); }
+
+template <bool SSE, bool SLIM, bool COMPACT = false>
+__global__ void __launch_bounds__(COMPACT ? kWsCompactThreads : kWsThreads, COMPACT ? 2 : kWsCtasPerSm)
 k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigned char *__restrict__ codes,
                    const unsigned char *__restrict__ raw, const u64 *__restrict__ peq, int hew_threshold,
                    int *__restrict__ bound, int *__restrict__ hew_out, u64 *__restrict__ counters,
-                   u64 *__restrict__ quad, const unsigned char *__restrict__ pair_odd)
+                   u64 *__restrict__ quad, const unsigned char *__restrict__ pair_odd, int only_flagged)
 {
-    __shared__ u64 s_weq[2 * kAlpha * kWsThreads];          // [2*5][T] window-aligned match masks
-    __shared__ u32 s_slim[SLIM ? 65 * kWsThreads : 1];      // [65][T] slim quadrant of full windows (see ws21_pair)
-    const int T = kWsThreads, t = threadIdx.x;
+    constexpr int T = COMPACT ? kWsCompactThreads : kWsThreads, NC = COMPACT ? 4 : kAlpha;
+    extern __shared__ __align__(16) unsigned char ws_smem[];
+    u64 *s_weq = reinterpret_cast<u64 *>(ws_smem);                         // [2 * NC][T] window-aligned match masks
+    u32 *s_slim = reinterpret_cast<u32 *>(ws_smem + (size_t)2 * NC * T * 8);  // SLIM: [65][T] slim quadrant of full windows (see ws21_pair)
+    const int t = threadIdx.x;
     u64 *weq = s_weq + t;
     const i64 gtid = (i64)blockIdx.x * T + t, nthr = (i64)gridDim.x * T;
     // Quadrant scratch of non-full and redone windows: [slot][resident thread] in HBM/L2 (reused window after window).
@@ -281,9 +296,11 @@ k_windowed21_score(const PairRec *__restrict__ pairs, int n_pairs, const unsigne
     const int hew_lim = 64 * hew_threshold / 100;            // (W-O)*64*thr/100, bpm_windowed.c:555
     u64 ws = 0;
     for (i64 i = gtid; i < n_pairs; i += nthr) {
+        const bool flagged = pair_odd[i] != 0;
+        if (COMPACT ? flagged : (only_flagged && !flagged)) continue;
         const PairRec pr = pairs[i];
         int score = 0, hew = 0;
-        ws21_pair<SSE, SLIM>(pr, codes, raw, peq, weq, qpv, qmv, nthr, s_slim + (SLIM ? t : 0), SLIM && pair_odd[i] == 0, hew_lim, score, hew, ws);
+        ws21_pair<SSE, SLIM, T, NC>(pr, codes, raw, peq, weq, qpv, qmv, nthr, s_slim + (SLIM ? t : 0), SLIM && !flagged, hew_lim, score, hew, ws);
         bound[i] = score;
         hew_out[i] = hew;
     }

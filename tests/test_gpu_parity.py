@@ -345,6 +345,34 @@ def test_stage1_bounds_match_oracle(oracle, fused, monkeypatch):
     a.close()
 
 
+def test_stage1_compact_kernel(oracle, monkeypatch):
+    """The COMPACT WindowEd(S) kernel (352-thread CTAs, four match-mask rows per word: the residency that makes 100 k pairs
+    one wave) forced on a small batch: plain pairs go through it, pairs with an N / lower-case / IUPAC character in the
+    text or an odd one in the pattern are left to the plain kernel; a pattern N stays in the compact kernel."""
+    import quicked_b200 as qb
+    monkeypatch.setenv("QB200_FUSED", "0")
+    monkeypatch.setenv("QB200_WS_COMPACT", "1")
+    rng = np.random.default_rng(5)
+    pairs = generate_pairs(300, 1500, 0.15, seed=91) + generate_pairs(40, 2000, 0.05, seed=92, indels=(6, 40)) + generate_pairs(60, 130, 0.1, seed=93)
+    pairs = [(p.encode() if isinstance(p, str) else p, t.encode() if isinstance(t, str) else t) for p, t in pairs]
+    for i in range(0, len(pairs), 7):                     # N in the pattern only
+        p = bytearray(pairs[i][0]); p[int(rng.integers(0, len(p)))] = ord("N"); pairs[i] = (bytes(p), pairs[i][1])
+    for i in range(3, len(pairs), 11):                    # N / odd characters in the text (the last one too: the look-ahead column)
+        t = bytearray(pairs[i][1])
+        for k in list(rng.integers(0, len(t), size=3)) + [len(t) - 1]:
+            t[k] = ord(rng.choice(list("Nna*R")))
+        pairs[i] = (pairs[i][0], bytes(t))
+    a = qb.BatchAligner(device=0)
+    for fs in (False, True):
+        res = a.align(pairs, algo=0, force_scalar=fs)
+        bound, hew = a.bounds()
+        for i, (p, t) in enumerate(pairs):
+            assert (int(bound[i]), int(hew[i])) == oracle.windowed_score(p, t, 2, 1, 40, not fs), (i, fs, len(p), len(t))
+        for i in range(0, len(pairs), 13):
+            assert res[i] == oracle.align(pairs[i][0], pairs[i][1], force_scalar=fs), i
+    a.close()
+
+
 def test_big_batch_with_odd_characters(oracle, monkeypatch):
     """>= 16 384 pairs take the thread-per-pattern match-mask builder and (unfused) the slim WindowEd path; a tenth of
     the pairs carry lower-case / IUPAC / other bytes, which must switch those pairs to the raw-byte compare"""

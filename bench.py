@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--bandwidth", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs in the CPU baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-packed", action="store_true", help="skip the 2-bit packed-input end-to-end leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -394,6 +395,43 @@ def main():
     assert np.array_equal(score_h, score), "end-to-end scores differ from the resident run"
     h2d_all, d2h_all = sum(all_ranks(float(st_e["h2d_bytes"]))), sum(all_ranks(float(st_e["d2h_bytes"])))
 
+    # ---- the same end-to-end call with the 2-bit packed input format (a quarter of the H2D bytes); the host packer runs
+    #      outside the timed region and is reported beside it ----
+    e2e_packed = None
+    if not args.no_packed:
+        t0 = time.perf_counter()
+        packed, ep, ec = qb.capi.pack_2bit(pinned, po, pl, to, tl)
+        pack_ms = 1e3 * (time.perf_counter() - t0)
+        ppin = lib.qb200_host_alloc(packed.size)
+        np.ctypeslib.as_array(C.cast(ppin, C.POINTER(C.c_uint8)), shape=(packed.size,))[:] = packed
+        pbatch = qb.capi.PackedBatch(ppin, int(pinned.size), n_pairs, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data,
+                                     ep.ctypes.data if ep.size else None, ec.ctypes.data if ec.size else None, int(ep.size))
+        score_p = np.empty(n_pairs, np.int32)
+        res_p = qb.capi.Results(score_p.ctypes.data, status_h.ctypes.data, cpin, cig_cap, off_h.ctypes.data, 0)
+
+        def packed_step():
+            rc = lib.qb200_align_batch_packed(gpu._h, C.byref(params), C.byref(pbatch), C.byref(res_p))
+            if rc != 0:
+                raise RuntimeError(f"qb200_align_batch_packed rc={rc}: {lib.qb200_last_error(gpu._h).decode()}")
+
+        for _ in range(max(1, args.warmup)):
+            packed_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            packed_step()
+        torch.cuda.synchronize()
+        dtp = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert np.array_equal(score_p, score), "packed-input scores differ from the resident run"
+        st_p = gpu.stats()
+        e2e_packed = {"value": job_pairs * args.steps / dtp, "unit": unit,
+                      "h2d_bytes_per_step": int(sum(all_ranks(float(st_p["h2d_bytes"])))),
+                      "d2h_bytes_per_step": int(sum(all_ranks(float(st_p["d2h_bytes"])))),
+                      "host_pack_ms_rank0": pack_ms, "exceptions_rank0": int(ep.size),
+                      "note": "qb200_align_batch_packed: 2-bit stream + exception list in pinned host memory in, host scores + CIGAR text out; packing (qb200_pack_batch, all host threads) is outside the timed region"}
+        lib.qb200_host_free(ppin)
+
     # ---- rooflines (the path is 64-bit bitwise work, bounded by the integer ALU issue rate) ----
     peaks, peak_kind = measured_peaks()
     stage_avg = {k: v / args.steps for k, v in stage.items() if k != "ms_total"}
@@ -463,7 +501,7 @@ def main():
                "data": "synthetic", "config": config,
                "gcups_equiv": value * length * length / 1e9,
                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all)},
-               "gpu_launches": int(launches), "host_affinity": numa, "roofline": roof, "int_alu_roofline": int_roof,
+               "e2e_packed": e2e_packed, "gpu_launches": int(launches), "host_affinity": numa, "roofline": roof, "int_alu_roofline": int_roof,
                "hbm_roofline": hbm_roof, "kernel_rooflines": roofs, "cpu_baseline": cpu, "parity": parity,
                "clocks": clocks, "stage_ms_per_step": stage_avg, "dominant_stage": dom,
                "rank_ms_per_step": rank_ms, "imbalance": max(rank_ms) / (sum(rank_ms) / len(rank_ms)),

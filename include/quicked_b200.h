@@ -103,6 +103,33 @@ int qb200_get_bounds(qb200_ctx_t *ctx, int32_t *bound, int32_t *high_error_windo
 int qb200_align_batch(qb200_ctx_t *ctx, const quicked_params_t *params,
                       const qb200_batch_t *host_batch, qb200_results_t *host_results);
 
+/* --- 2-bit packed input (BASELINE north_star design 3): a quarter of the bytes over PCIe ---
+ * The character stream of a qb200_batch_t with 4 characters per byte: character i sits in bits 2*(i&3) .. 2*(i&3)+1 of
+ * packed[i>>2], A = 0, C = 1, G = 2, T = 3 (upper case).  Every other byte INSIDE a sequence (N, lower case, IUPAC, ...)
+ * is stored as 0 and listed as an exception (exc_pos ascending = character index, exc_chr = the raw byte), so the
+ * alignment sees exactly the caller's characters (reference dna_text.c:41-46 and the raw-byte compares of the
+ * tracebacks).  Offsets are character indices into the stream; bytes between sequences are not kept.
+ * The device expands the stream back to the ASCII buffer the kernels read (k_unpack2 / k_patch_exceptions). */
+typedef struct {
+    const uint8_t *packed;        /* [(n_chars + 3) / 4]                                 */
+    int64_t        n_chars;
+    int64_t        n_pairs;
+    const int64_t *pattern_off;   /* [n_pairs] character index                           */
+    const int32_t *pattern_len;
+    const int64_t *text_off;
+    const int32_t *text_len;
+    const int64_t *exc_pos;       /* [n_exc] ascending character indices                 */
+    const uint8_t *exc_chr;       /* [n_exc] the raw bytes there                         */
+    int64_t        n_exc;
+} qb200_packed_batch_t;
+/* Host packer: characters of `in` -> packed (capacity >= (in->seqs_bytes + 3) / 4 + 8 bytes) + exception list; character
+ * index = byte index of in->seqs, so in's offset / length arrays serve the packed batch unchanged.  `threads` host threads
+ * (<= 0: all).  Returns the number of exceptions, or -(number needed) when exc_cap is too small, or QB200_ERR_ARG. */
+int64_t qb200_pack_batch(const qb200_batch_t *in, uint8_t *packed, int64_t *exc_pos, uint8_t *exc_chr, int64_t exc_cap, int threads);
+int qb200_upload_packed(qb200_ctx_t *ctx, const qb200_packed_batch_t *host_batch);           /* then qb200_run / qb200_download */
+int qb200_align_batch_packed(qb200_ctx_t *ctx, const quicked_params_t *params,
+                             const qb200_packed_batch_t *host_batch, qb200_results_t *host_results);
+
 /* --- measured integer-ALU peak (LOP3+IADD3 mix, no memory traffic), in 10^12 int32 ops/s: the denominator of the
  * bit-op roofline (MEASURED_PEAKS.json carries only HBM and bf16 peaks) --- */
 int qb200_measure_int_peak(qb200_ctx_t *ctx, double *tera_ops_per_s);

@@ -26,7 +26,8 @@ EXPORTS = ["quicked_check_error", "quicked_status_msg", "quicked_default_params"
            "quicked_align", "qb200_device_count", "qb200_create", "qb200_destroy", "qb200_set_stream",
            "qb200_set_workspace_limit", "qb200_last_error", "qb200_upload", "qb200_upload_device", "qb200_run",
            "qb200_download", "qb200_get_stats", "qb200_get_bounds", "qb200_cigar_to_sam", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
-           "qb200_generate_pairs", "qb200_generate_pairs_ex", "qb200_measure_int_peak"]
+           "qb200_generate_pairs", "qb200_generate_pairs_ex", "qb200_measure_int_peak", "qb200_pack_batch", "qb200_upload_packed",
+           "qb200_align_batch_packed"]
 
 
 class Params(C.Structure):        # quicked_params_t, 48 bytes
@@ -44,6 +45,12 @@ class Aligner(C.Structure):       # quicked_aligner_t, 72 bytes
 class Batch(C.Structure):         # qb200_batch_t
     _fields_ = [("seqs", C.c_void_p), ("seqs_bytes", C.c_int64), ("n_pairs", C.c_int64), ("pattern_off", C.c_void_p),
                 ("pattern_len", C.c_void_p), ("text_off", C.c_void_p), ("text_len", C.c_void_p)]
+
+
+class PackedBatch(C.Structure):   # qb200_packed_batch_t
+    _fields_ = [("packed", C.c_void_p), ("n_chars", C.c_int64), ("n_pairs", C.c_int64), ("pattern_off", C.c_void_p),
+                ("pattern_len", C.c_void_p), ("text_off", C.c_void_p), ("text_len", C.c_void_p), ("exc_pos", C.c_void_p),
+                ("exc_chr", C.c_void_p), ("n_exc", C.c_int64)]
 
 
 class Results(C.Structure):       # qb200_results_t
@@ -99,6 +106,10 @@ def load():
     L.qb200_cigar_to_sam.restype = C.c_int64
     L.qb200_cigar_to_sam.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
     L.qb200_align_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Batch), C.POINTER(Results)]
+    L.qb200_pack_batch.restype = C.c_int64
+    L.qb200_pack_batch.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    L.qb200_upload_packed.argtypes = [C.c_void_p, C.POINTER(PackedBatch)]
+    L.qb200_align_batch_packed.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PackedBatch), C.POINTER(Results)]
     L.qb200_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qb200_host_alloc.restype = C.c_void_p
     L.qb200_host_alloc.argtypes = [C.c_size_t]
@@ -292,19 +303,83 @@ class BatchAligner:
             out.append((int(status[i]), int(score[i]), c))
         return out
 
+    def upload_packed_arrays(self, packed, n_chars, po, pl, to, tl, exc_pos, exc_chr):
+        """2-bit packed stream + exception list (pack_2bit) -> qb200_upload_packed"""
+        self._keep = (packed, po, pl, to, tl, exc_pos, exc_chr)
+        b = PackedBatch(packed.ctypes.data, int(n_chars), int(po.size), po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data,
+                        exc_pos.ctypes.data if exc_pos.size else None, exc_chr.ctypes.data if exc_chr.size else None, int(exc_pos.size))
+        self._n = int(po.size)
+        self._check(self._lib.qb200_upload_packed(self._h, C.byref(b)), "qb200_upload_packed")
+
+    def align_packed(self, pairs, params=None, **kw):
+        """align(pairs) through the 2-bit packed upload"""
+        seqs, po, pl, to, tl = pack_pairs(pairs)
+        packed, ep, ec = pack_2bit(seqs, po, pl, to, tl)
+        self.upload_packed_arrays(packed, int(seqs.size), po, pl, to, tl, ep, ec)
+        return self._finish(len(pairs), params, **kw)
+
+    def align_batch_packed(self, pairs, params=None, **kw):
+        """qb200_align_batch_packed (2-bit packed host input, host out; pipelined for big jobs)"""
+        seqs, po, pl, to, tl = pack_pairs(pairs)
+        packed, ep, ec = pack_2bit(seqs, po, pl, to, tl)
+        n = int(po.size)
+        p = params if params is not None else make_params(**kw)
+        score = np.empty(n, np.int32); status = np.empty(n, np.int32); off = np.zeros(n + 1, np.int64)
+        b = PackedBatch(packed.ctypes.data, int(seqs.size), n, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data,
+                        ep.ctypes.data if ep.size else None, ec.ctypes.data if ec.size else None, int(ep.size))
+        cig = np.zeros(int(seqs.size) // 2 + 1024, np.uint8)
+        for _ in range(2):
+            r = Results(score.ctypes.data, status.ctypes.data, cig.ctypes.data, int(cig.size), off.ctypes.data, 0)
+            rc = self._lib.qb200_align_batch_packed(self._h, C.byref(p), C.byref(b), C.byref(r))
+            if rc != QB200_ERR_CAPACITY:
+                break
+            cig = np.zeros(int(r.cigar_bytes) + 16, np.uint8)
+        self._check(rc, "qb200_align_batch_packed")
+        raw = cig.tobytes()
+        return [(int(status[i]), int(score[i]), raw[off[i]:off[i + 1] - 1].decode() if off[i + 1] - off[i] > 1 else None) for i in range(n)]
+
     def align(self, pairs, params=None, **kw):
         """-> list of (status, score, cigar-or-None), one tuple per pair"""
         self.upload_arrays(*pack_pairs(pairs))
+        return self._finish(len(pairs), params, **kw)
+
+    def _finish(self, n_pairs, params=None, **kw):
         self.run(params, **kw)
         status, score, off, cig = self.download()
         out = []
         raw = cig.tobytes() if cig is not None else b""
-        for i in range(len(pairs)):
+        for i in range(n_pairs):
             c = None
             if cig is not None and off[i + 1] - off[i] > 1:
                 c = raw[off[i]:off[i + 1] - 1].decode()
             out.append((int(status[i]), int(score[i]), c))
         return out
+
+
+def pack_2bit(seqs, po, pl, to, tl, threads=0):
+    """Host packer qb200_pack_batch: the ASCII batch (numpy arrays of pack_pairs / generate_pairs_native) ->
+    (packed uint8[(n+3)//4 + 8], exc_pos int64[], exc_chr uint8[]); the offset / length arrays serve both formats."""
+    L = load()
+    b = Batch(seqs.ctypes.data, int(seqs.size), int(po.size), po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data)
+    packed = np.zeros((int(seqs.size) + 3) // 4 + 8, np.uint8)
+    cap = 1024
+    while True:
+        ep = np.zeros(cap, np.int64); ec = np.zeros(cap, np.uint8)
+        ne = L.qb200_pack_batch(C.byref(b), packed.ctypes.data, ep.ctypes.data, ec.ctypes.data, cap, int(threads))
+        if ne >= 0:
+            return packed, ep[:ne].copy(), ec[:ne].copy()
+        if ne <= -100:
+            raise RuntimeError(f"qb200_pack_batch rc={ne}")
+        cap = -ne + 16
+
+
+def unpack_2bit(packed, n_chars, exc_pos, exc_chr):
+    """numpy restatement of the device unpack (k_unpack2 + k_patch_exceptions): the characters the kernels will see"""
+    idx = np.arange(n_chars)
+    codes = (packed[idx >> 2] >> (2 * (idx & 3))) & 3
+    out = np.frombuffer(b"ACGT", np.uint8)[codes].copy()
+    out[exc_pos] = exc_chr
+    return out
 
 
 def cigar_to_sam(cigar, show_mismatches=False):

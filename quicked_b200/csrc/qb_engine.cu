@@ -122,6 +122,7 @@ struct qb200_ctx {
     DevBuf d_cls, d_cutoff, d_plan_items, d_plan_offs, d_textbytes, d_list_t, d_list_w, d_list_slow, d_gsize, d_goff, d_gB;
     unsigned char *h_pinned = nullptr;     // small pinned mailbox for totals
     DevBuf d_quad;                         // WindowEd(S) quadrant scratch
+    DevBuf d_packed, d_excpos, d_excchr;   // 2-bit packed upload: the stream and its exception list
     DevBuf d_fmat, d_franges, d_done;      // fused fast path: per-resident-warp matrix slots, live ranges, per-pair done flags
     i64 ops_words_fused = 0;               // op words of all pairs (fused-path region of the op pool)
     int max_n = 0, max_m = 0;
@@ -593,7 +594,7 @@ void qb200_destroy(qb200_ctx_t *ctx)
                       &ctx->d_matrix, &ctx->d_scores, &ctx->d_state, &ctx->d_ops, &ctx->d_ranges, &ctx->d_cls, &ctx->d_cutoff,
                       &ctx->d_plan_items, &ctx->d_plan_offs, &ctx->d_textbytes, &ctx->d_list_t, &ctx->d_list_w, &ctx->d_list_slow,
                       &ctx->d_gsize, &ctx->d_goff, &ctx->d_gB, &ctx->d_peq2, &ctx->d_jobs2, &ctx->d_tasks2, &ctx->d_wintasks,
-                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter, &ctx->d_tclass, &ctx->d_tctl, &ctx->d_punt, &ctx->d_gather, &ctx->d_ttext, &ctx->d_wintile})
+                      &ctx->d_quad, &ctx->d_fmat, &ctx->d_franges, &ctx->d_done, &ctx->d_winout, &ctx->d_winscratch, &ctx->d_split, &ctx->d_splitout, &ctx->d_splitscratch, &ctx->d_scatter, &ctx->d_tclass, &ctx->d_tctl, &ctx->d_punt, &ctx->d_gather, &ctx->d_ttext, &ctx->d_wintile, &ctx->d_packed, &ctx->d_excpos, &ctx->d_excchr})
         b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     ctx->h_pairs.release();
@@ -648,6 +649,146 @@ int qb200_upload(qb200_ctx_t *ctx, const qb200_batch_t *b)
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
     ctx->stats.h2d_bytes += b->seqs_bytes;
     return finish_upload(ctx);
+}
+
+// ---- 2-bit packed input ----
+__global__ void __launch_bounds__(256) k_unpack2(const u32 *__restrict__ packed, uint4 *__restrict__ raw, i64 nvec)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const u32 w = __ldg(packed + i);                      // 16 characters
+    u32 o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        u32 v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v |= ((0x54474341u >> (8 * ((w >> (8 * k + 2 * j)) & 3u))) & 0xffu) << (8 * j);   // "ACGT"[code]
+        o[k] = v;
+    }
+    raw[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+__global__ void __launch_bounds__(256) k_patch_exceptions(const i64 *__restrict__ pos, const unsigned char *__restrict__ chr, i64 n, unsigned char *__restrict__ raw)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) raw[pos[i]] = chr[i];
+}
+
+int64_t qb200_pack_batch(const qb200_batch_t *in, uint8_t *packed, int64_t *exc_pos, uint8_t *exc_chr, int64_t exc_cap, int threads)
+{
+    if (!in || !packed || in->seqs_bytes < 0 || in->n_pairs < 0 || exc_cap < 0) return QB200_ERR_ARG;
+    const i64 n = in->n_pairs, nb = in->seqs_bytes, nq = (nb + 3) / 4;
+    for (i64 i = 0; i < n; ++i) {
+        const i64 po = in->pattern_off[i], to = in->text_off[i], m = in->pattern_len[i], t = in->text_len[i];
+        if (m < 0 || t < 0 || po < 0 || to < 0 || po + m > nb || to + t > nb) return QB200_ERR_ARG;
+    }
+    int nt = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    nt = (int)std::max<i64>(1, std::min<i64>(nt, nq / (1 << 16) + 1));
+    // 1) the stream, four characters per byte (anything that is not ACGT packs as 0)
+    {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back([=]() {
+            const i64 q0 = nq * k / nt, q1 = nq * (k + 1) / nt;
+            const unsigned char *s = reinterpret_cast<const unsigned char *>(in->seqs);
+            for (i64 q = q0; q < q1; ++q) {
+                unsigned v = 0;
+                const i64 lim = std::min<i64>(4, nb - 4 * q);
+                for (i64 j = 0; j < lim; ++j) {
+                    const unsigned c = s[4 * q + j];
+                    // A 0x41 C 0x43 G 0x47 T 0x54: bits 1-2 of the byte are 0, 1, 3, 2
+                    const unsigned code = (c >> 1) & 3u;
+                    v |= (code ^ (code >> 1)) << (2 * j);
+                }
+                packed[q] = (uint8_t)v;
+            }
+        });
+        for (auto &t : th) t.join();
+    }
+    // 2) the exceptions, pair by pair (pairs are scanned in index order; the list is sorted afterwards if the batch is not)
+    std::vector<std::vector<std::pair<i64, uint8_t>>> found((size_t)nt);
+    {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back([=, &found]() {
+            const i64 i0 = n * k / nt, i1 = n * (k + 1) / nt;
+            const unsigned char *s = reinterpret_cast<const unsigned char *>(in->seqs);
+            auto &out = found[(size_t)k];
+            auto scan = [&](i64 off, i64 len) {
+                for (i64 j = off; j < off + len; ++j) {
+                    const unsigned c = s[j];
+                    if (c != 'A' && c != 'C' && c != 'G' && c != 'T') out.emplace_back(j, (uint8_t)c);
+                }
+            };
+            for (i64 i = i0; i < i1; ++i) { scan(in->pattern_off[i], in->pattern_len[i]); scan(in->text_off[i], in->text_len[i]); }
+        });
+        for (auto &t : th) t.join();
+    }
+    std::vector<std::pair<i64, uint8_t>> all;
+    for (auto &f : found) all.insert(all.end(), f.begin(), f.end());
+    if (!std::is_sorted(all.begin(), all.end())) std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());          // sequences may overlap (shared texts)
+    const i64 ne = (i64)all.size();
+    if (ne > exc_cap || (ne > 0 && (!exc_pos || !exc_chr))) return -std::max<i64>(ne, 1);
+    for (i64 k = 0; k < ne; ++k) {
+        exc_pos[k] = all[(size_t)k].first; exc_chr[k] = all[(size_t)k].second;
+        packed[exc_pos[k] >> 2] &= (uint8_t)~(3u << (2 * (exc_pos[k] & 3)));      // exceptions pack as 0
+    }
+    return ne;
+}
+
+int qb200_upload_packed(qb200_ctx_t *ctx, const qb200_packed_batch_t *b)
+{
+    if (!ctx || !b || b->n_pairs < 0 || b->n_chars < 0 || b->n_exc < 0) return QB200_ERR_ARG;
+    if (b->n_pairs > kMaxPairs) { ctx->err = "a batch holds at most 2^31 - 2^20 pairs: split it"; return QB200_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_pairs = b->n_pairs; ctx->raw_bytes = b->n_chars; ctx->d_raw_ext = nullptr;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    const size_t padded = ((size_t)b->n_chars + 15) / 16 * 16 + 48;
+    const i64 nvec = (i64)((b->n_chars + 15) / 16);
+    CK(ctx->d_raw.reserve(padded));
+    CK(ctx->d_packed.reserve((size_t)nvec * 4 + 16));
+    CK(cudaMemsetAsync(ctx->d_raw.as<char>() + (padded - 48), 0, 48, ctx->stream));
+    const size_t pbytes = (size_t)(b->n_chars + 3) / 4;
+    if (pbytes) {
+        CK(cudaMemsetAsync(ctx->d_packed.as<char>() + (size_t)nvec * 4 - 4, 0, 4, ctx->stream));       // the last word may be partial
+        CK(cudaMemcpyAsync(ctx->d_packed.p, b->packed, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+        k_unpack2<<<(unsigned)((nvec + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_packed.as<u32>(), ctx->d_raw.as<uint4>(), nvec);
+    }
+    for (i64 k = 0; k < b->n_exc; ++k)
+        if (b->exc_pos[k] < 0 || b->exc_pos[k] >= b->n_chars) { cudaStreamSynchronize(ctx->stream); ctx->err = "exception position outside the stream"; return QB200_ERR_ARG; }
+    if (b->n_exc) {
+        CK(ctx->d_excpos.reserve((size_t)b->n_exc * 8));
+        CK(ctx->d_excchr.reserve((size_t)b->n_exc));
+        CK(cudaMemcpyAsync(ctx->d_excpos.p, b->exc_pos, (size_t)b->n_exc * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_excchr.p, b->exc_chr, (size_t)b->n_exc, cudaMemcpyHostToDevice, ctx->stream));
+        k_patch_exceptions<<<(unsigned)((b->n_exc + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_excpos.as<i64>(), ctx->d_excchr.as<unsigned char>(), b->n_exc,
+                                                                                      ctx->d_raw.as<unsigned char>());
+    }
+    CK(cudaGetLastError());
+    int rc = build_pair_records(ctx, b->n_pairs, b->pattern_off, b->pattern_len, b->text_off, b->text_len, b->n_chars);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    ctx->stats.h2d_bytes += (i64)pbytes + b->n_exc * 9;
+    return finish_upload(ctx);
+}
+
+static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res,
+                                 const qb200_packed_batch_t *pk);
+
+int qb200_align_batch_packed(qb200_ctx_t *ctx, const quicked_params_t *params, const qb200_packed_batch_t *b, qb200_results_t *res)
+{
+    if (!ctx || !params || !b || !res) return QB200_ERR_ARG;
+    // big jobs are pipelined like qb200_align_batch's (the thresholds count characters, not packed bytes: what a sub-batch
+    // costs on the device is the same)
+    i64 min_pairs = 200000;
+    if (const char *e = getenv("QB200_PIPELINE_MIN_PAIRS")) min_pairs = std::max<i64>(2, atoll(e));
+    const bool big = b->n_pairs >= min_pairs || (b->n_pairs >= 4096 && b->n_chars >= ((i64)512 << 20));
+    if (big && !getenv("QB200_NO_PIPELINE")) {
+        for (i64 k = 1; k < b->n_exc; ++k) if (b->exc_pos[k - 1] >= b->exc_pos[k]) { ctx->err = "exception positions must ascend"; return QB200_ERR_ARG; }
+        const qb200_batch_t view = {nullptr, b->n_chars, b->n_pairs, b->pattern_off, b->pattern_len, b->text_off, b->text_len};
+        return align_batch_pipelined(ctx, params, &view, res, b);
+    }
+    int rc = qb200_upload_packed(ctx, b);
+    if (!rc) rc = qb200_run(ctx, params);
+    if (!rc) rc = qb200_download(ctx, res);
+    return rc;
 }
 
 int qb200_upload_device(qb200_ctx_t *ctx, const qb200_batch_t *b)
@@ -1820,7 +1961,11 @@ int qb200_measure_int_peak(qb200_ctx_t *ctx, double *tera_ops_per_s)
 //   compute thread   : kernels of sub-batch k-1            (the GPU runs one sub-batch at a time, at full occupancy)
 //   downloader thread: D2H of sub-batch k-2 into the caller's buffers (PCIe device->host, full duplex with the upload)
 // CIGAR strings stay packed in input order: the compute thread knows the text bytes of every earlier sub-batch.
-static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res)
+// pk != nullptr: the characters come as a 2-bit packed stream (b then only carries the offset / length arrays and
+// seqs_bytes = the stream's character count); sub-batches start on a packed byte (4 characters) and take their slice of
+// the exception list.
+static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params, const qb200_batch_t *b, qb200_results_t *res,
+                                 const qb200_packed_batch_t *pk = nullptr)
 {
     const i64 n = b->n_pairs;
     if (n > kMaxPairs) { ctx->err = "a batch holds at most 2^31 - 2^20 pairs: split it"; return QB200_ERR_ARG; }
@@ -1884,7 +2029,7 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
 
     std::thread uploader([&] {
         cudaSetDevice(ctx->device);
-        std::vector<int64_t> po, to;
+        std::vector<int64_t> po, to, epos;
         for (int k = 0; k < S; ++k) {
             {
                 std::unique_lock<std::mutex> lk(mu);
@@ -1900,10 +2045,21 @@ static int align_batch_pipelined(qb200_ctx *ctx, const quicked_params_t *params,
                 hi = std::max<i64>(hi, std::max<i64>(b->pattern_off[i] + b->pattern_len[i], b->text_off[i] + b->text_len[i]));
             }
             if (hi < lo) { lo = 0; hi = 0; }
+            if (pk) lo &= ~(i64)3;                            // a packed sub-batch starts on a byte of the stream
             po.resize((size_t)cnt); to.resize((size_t)cnt);
             for (i64 i = 0; i < cnt; ++i) { po[(size_t)i] = b->pattern_off[i0 + i] - lo; to[(size_t)i] = b->text_off[i0 + i] - lo; }
-            qb200_batch_t sb = {b->seqs + lo, hi - lo, cnt, po.data(), b->pattern_len + i0, to.data(), b->text_len + i0};
-            const int rc = qb200_upload(c, &sb);
+            int rc;
+            if (pk) {
+                const int64_t *e0 = std::lower_bound(pk->exc_pos, pk->exc_pos + pk->n_exc, lo), *e1 = std::lower_bound(e0, pk->exc_pos + pk->n_exc, hi);
+                epos.assign(e0, e1);
+                for (auto &x : epos) x -= lo;
+                qb200_packed_batch_t sp = {pk->packed + lo / 4, hi - lo, cnt, po.data(), b->pattern_len + i0, to.data(), b->text_len + i0,
+                                           epos.data(), pk->exc_chr + (e0 - pk->exc_pos), (int64_t)epos.size()};
+                rc = qb200_upload_packed(c, &sp);
+            } else {
+                qb200_batch_t sb = {b->seqs + lo, hi - lo, cnt, po.data(), b->pattern_len + i0, to.data(), b->text_len + i0};
+                rc = qb200_upload(c, &sb);
+            }
             if (rc) { fail(rc, c); return; }
             if (trace) fprintf(stderr, "[qb200 pipeline] sub %d uploaded in %.2f ms\n", k, t_ms(t0));
             { std::lock_guard<std::mutex> lk(mu); uploaded = k + 1; }

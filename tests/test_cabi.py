@@ -189,3 +189,31 @@ def test_bench_helpers(oracle):
     for j, i in enumerate(sel):
         assert bytes(s2[po2[j]:po2[j] + pl2[j]]) == bytes(s[po[i]:po[i] + pl[i]])
         assert bytes(s2[to2[j]:to2[j] + tl2[j]]) == bytes(s[to[i]:to[i] + tl[i]])
+
+
+def test_pack_2bit_round_trip(lib):
+    """Host packer of the 2-bit upload format (qb200_pack_batch): unpacking the stream and patching the exception list
+    (numpy restatement of the device kernels) gives back every sequence byte for byte — N, lower case, IUPAC and other
+    bytes included; bytes between sequences are not kept."""
+    import numpy as np
+    from quicked_b200 import capi
+    from quicked_b200.datagen import generate_pairs
+    rng = np.random.default_rng(3)
+    pairs = generate_pairs(50, 333, 0.1, seed=5) + generate_pairs(3, 5, 0.2, seed=6) + [("", "ACGT"), ("A", "")]
+    pairs = [(p.encode() if isinstance(p, str) else p, t.encode() if isinstance(t, str) else t) for p, t in pairs]
+    for i in range(0, len(pairs), 3):
+        p, t = bytearray(pairs[i][0]), bytearray(pairs[i][1])
+        for buf in (p, t):
+            for k in rng.integers(0, max(1, len(buf)), size=4):
+                if len(buf):
+                    buf[k] = int(rng.choice(list(b"NnacgtRY*-\xff")))
+        pairs[i] = (bytes(p), bytes(t))
+    seqs, po, pl, to, tl = capi.pack_pairs(pairs)
+    for threads in (1, 4):
+        packed, ep, ec = capi.pack_2bit(seqs, po, pl, to, tl, threads=threads)
+        assert np.all(np.diff(ep) > 0)
+        back = capi.unpack_2bit(packed, int(seqs.size), ep, ec)
+        for i, (p, t) in enumerate(pairs):
+            assert bytes(back[po[i]:po[i] + pl[i]]) == p and bytes(back[to[i]:to[i] + tl[i]]) == t, i
+        n_exc = sum(sum(c not in b"ACGT" for c in p) + sum(c not in b"ACGT" for c in t) for p, t in pairs)
+        assert ep.size == n_exc

@@ -373,6 +373,36 @@ def test_stage1_compact_kernel(oracle, monkeypatch):
     a.close()
 
 
+def test_packed_upload_matches_ascii_upload(oracle, monkeypatch):
+    """2-bit packed input (qb200_pack_batch -> qb200_upload_packed): same scores and CIGARs as the ASCII upload and the
+    oracle, on plain reads and on reads with N / lower-case / IUPAC characters (the exception list)."""
+    import quicked_b200 as qb
+    rng = np.random.default_rng(11)
+    pairs = generate_pairs(120, 700, 0.12, seed=31) + generate_pairs(20, 5000, 0.2, seed=32) + generate_pairs(60, 90, 0.05, seed=33)
+    pairs = [(p.encode() if isinstance(p, str) else p, t.encode() if isinstance(t, str) else t) for p, t in pairs]
+    for i in range(0, len(pairs), 5):
+        p, t = bytearray(pairs[i][0]), bytearray(pairs[i][1])
+        for buf in (p, t):
+            for k in rng.integers(0, len(buf), size=5):
+                buf[k] = ord(rng.choice(list(chr(buf[k]).lower() + "NRn*")))
+        pairs[i] = (bytes(p), bytes(t))
+    a = qb.BatchAligner(device=0)
+    for algo in (0, 2):
+        got = a.align_packed(pairs, algo=algo)
+        assert got == a.align(pairs, algo=algo)
+        for i in range(0, len(pairs), 9):
+            assert got[i] == oracle.align(pairs[i][0], pairs[i][1], algo=algo), (algo, i)
+    # the pipelined form: sub-batches start on a packed byte and take their slice of the exception list
+    monkeypatch.setenv("QB200_PIPELINE_MIN_PAIRS", "64")
+    monkeypatch.setenv("QB200_SUB_PAIRS", "1024")
+    many = generate_pairs(3000, 151, 0.1, seed=34)
+    many = [(p.encode() if isinstance(p, str) else p, t.encode() if isinstance(t, str) else t) for p, t in many]
+    for i in range(0, len(many), 17):
+        t = bytearray(many[i][1]); t[int(rng.integers(0, len(t)))] = ord("N"); many[i] = (many[i][0], bytes(t))
+    assert a.align_batch_packed(many + pairs, algo=0) == a.align(many + pairs, algo=0)
+    a.close()
+
+
 def test_big_batch_with_odd_characters(oracle, monkeypatch):
     """>= 16 384 pairs take the thread-per-pattern match-mask builder and (unfused) the slim WindowEd path; a tenth of
     the pairs carry lower-case / IUPAC / other bytes, which must switch those pairs to the raw-byte compare"""

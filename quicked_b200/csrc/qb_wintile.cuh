@@ -20,6 +20,7 @@
 // with the SSE quirks.  The kernel flags those tasks (WinOut.hew = kWinPunted) and the warp kernel picks them up.
 #pragma once
 #include "qb_tiles.cuh"
+#include "qb_tiletrace.cuh"
 #include "qb_windowed.cuh"
 
 namespace qb {
@@ -141,49 +142,40 @@ k_windowed_tiles(const WinTask *__restrict__ tasks, int n_tasks, const unsigned 
                 if (k != txt_k) { stage_text(h0 + 64 * k, min(64, cols - 64 * k)); txt_k = k; }
                 const ulonglong2 ra = rec_a[(k * W + b) * nthr], rb = rec_b[(k * W + b) * nthr];
                 u64 pv = ra.x, mv = ra.y;
-                u32 wp = (u32)rb.x, wm = (u32)rb.y;
                 const int lo0 = r0 - s0 - kTraceHalfW;                   // lowest slice row at column 0
-                const int s_need = s0 - r0 - kTraceHalfW;                // the walk cannot reach columns below this
-                u64 cw = txt[0];
+                // all 64 columns in groups of eight, every column with its planes (qb_tiletrace.cuh: a trip count or a
+                // "planes needed?" test that depends on the pair makes the lanes of a warp take turns); columns past the
+                // window hold code 4 and are never read by the walk
 #pragma unroll 1
-                for (int s = 0; s <= s0; ++s) {
-                    if ((s & 7) == 0 && s) cw = txt[(s >> 3) * T];
-                    if (s == 32) { wp = (u32)(rb.x >> 32); wm = (u32)(rb.y >> 32); }
-                    const u64 e = eq[(unsigned)(cw & 7u) * T];
-                    cw >>= 8;
-                    const u64 mv_old = mv;
-                    {
-                        const u64 xv = e | mv;
-                        const u64 eqh = e | (u64)(wm >> 31);
-                        const u64 xh = (((eqh & pv) + pv) ^ pv) | eqh;
-                        u64 ph = mv | ~(xh | pv);
-                        u64 mh = pv & xh;
-                        ph = (ph << 1) | (u64)(wp >> 31);
-                        mh = (mh << 1) | (u64)(wm >> 31);
-                        wp <<= 1; wm <<= 1;
-                        pv = mh | ~(xv | ph);
-                        mv = ph & xv;
-                    }
-                    if (s >= s_need) {
+                for (int s8 = 0; s8 < 64; s8 += 8) {
+                    u64 cw = txt[(s8 >> 3) * T];
+                    u32 wp = (u32)(s8 < 32 ? rb.x : rb.x >> 32) << (s8 & 31), wm = (u32)(s8 < 32 ? rb.y : rb.y >> 32) << (s8 & 31);
+                    u32 *pl = planes + s8 * T;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const u64 e = eq[(unsigned)(cw & 7u) * T];
+                        cw >>= 8;
+                        const u64 mv_old = mv;
+                        QB_TRACE_STEP(e);
                         u64 pa, pb;
                         if (SCORE_ONLY) { pa = pv | ~(mv_old | e); pb = ~pv & (mv_old | ~e); }      // D (1,0)  I (0,1)  X (1,1)  M (0,0)
                         else { pa = ~e & (pv | ~mv_old); pb = ~e & ~pv; }                          // M first: (0,0) whenever the characters match
-                        planes[s * T] = win_slice16(pa, lo0 + s) | (win_slice16(pb, lo0 + s) << 16);
+                        const int lo = trace_slice_lo(lo0, s8 + i);
+                        pl[i * T] = __byte_perm((u32)(pa >> lo), (u32)(pb >> lo), 0x5410);
                     }
                 }
-                int rr = r0, s = s0;
+                int rr = r0, s = s0, qd = kTraceHalfW;                   // qd: row - (diagonal - kTraceHalfW), the unclamped slice index
                 const int r_stop = v_stop - v0 - 64 * b, s_stop = h_stop - h0 - 64 * k;   // walk limits in tile coordinates
-                for (;;) {
-                    if (rr < 0 || s < 0 || rr < r_stop || s < s_stop) break;
-                    const int qd = (rr - r0) + (s0 - s) + kTraceHalfW;
-                    if (qd < 0 || qd > 15) break;
-                    const u32 wd = planes[s * T];
-                    const u32 a = (wd >> qd) & 1u, bb = (wd >> (16 + qd)) & 1u;
-                    const int op = a ? (bb ? OP_X : OP_D) : (bb ? OP_I : OP_M);
-                    if (SCORE_ONLY) cost += (op != OP_M);
+                const int r_lim = max(r_stop, 0), s_lim = max(s_stop, 0);
+                while (rr >= r_lim && s >= s_lim && (unsigned)qd <= 15u) {
+                    const u32 t2 = (planes[s * T] >> (rr - trace_slice_lo(lo0, s))) & 0x10001u;
+                    const u32 a = t2 & 1u, bb = t2 >> 16;
+                    const int op = (int)(((a ^ bb) << 1) | a);             // (1,0) D = 3, (0,1) I = 2, (1,1) X = 1, (0,0) M = 0
+                    if (SCORE_ONLY) cost += (int)(a | bb);
                     else ow.emit(op);
-                    rr -= (op != OP_I) ? 1 : 0;
-                    s -= (op != OP_D) ? 1 : 0;
+                    qd += (int)bb - (int)a;
+                    rr -= (int)(1u - (bb & ~a));
+                    s -= (int)(1u - (a & ~bb));
                 }
                 v = v0 + 64 * b + rr;
                 h = h0 + 64 * k + s;

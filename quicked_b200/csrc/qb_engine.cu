@@ -949,6 +949,34 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         ctx->stats.matrix_bytes += 0;
         leaf_base = n; ops_base = ctx->ops_words_fused;
     }
+    // ---- WINDOWED with CIGAR: planned and run on the device (tasks, pseudo-leaves and leaf lists from the pair records;
+    //      the tile kernel; pairs it leaves to the warp kernel — odd characters — take the host-driven path below) ----
+    const bool win_fast = prm.algo == WINDOWED && !prm.only_score && ctx->use_tiles && prm.window_size >= 1 && prm.window_size <= 32 &&
+                          prm.overlap_size < prm.window_size && !(prm.window_size == 2 && !prm.force_scalar) && !getenv("QB200_WIN_HOST");
+    if (win_fast) {
+        if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+        const int W = (int)prm.window_size;
+        const int blocks = (int)std::min<i64>((n + kWtThreads - 1) / kWtThreads, (i64)ctx->sms * 4);
+        const i64 nthr = (i64)blocks * kWtThreads, rec_tiles = (i64)W * W;
+        CK(ctx->d_wintile.reserve((size_t)((2 * rec_tiles + W) * nthr) * 16 + 64));
+        CK(ctx->d_wintasks.reserve(sizeof(WinTask) * (size_t)n));
+        CK(ctx->d_winout.reserve(sizeof(WinOut) * (size_t)n));
+        CK(ctx->d_done.reserve((size_t)n));
+        CK(ctx->d_leaves.reserve(sizeof(BandTask) * (size_t)n));
+        CK(ctx->d_leafout.reserve(sizeof(LeafOut) * (size_t)n));
+        CK(ctx->d_ops.reserve((size_t)std::max<i64>(ctx->ops_words_fused, 1) * 4 + 16));
+        Span sp(ctx, ST_WL);
+        k_win_build<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, W, (int)prm.overlap_size, prm.force_scalar ? 0 : 1, ctx->d_wintasks.as<WinTask>(),
+                                                    ctx->d_leaves.as<BandTask>(), ctx->d_pairleaves.as<PairLeaves>(), ctx->d_status.as<int>(), QUICKED_WIP);
+        k_windowed_tiles<false><<<blocks, kWtThreads, 0, ctx->stream>>>(ctx->d_wintasks.as<WinTask>(), ni, ctx->d_codes.as<unsigned char>(), ctx->d_peq.as<u64>(),
+            ctx->d_wintile.as<ulonglong2>(), rec_tiles, W, ctx->d_ops.as<u32>(), ctx->d_winout.as<WinOut>(), ctx->d_leafout.as<LeafOut>(), ctx->d_counters.as<u64>());
+        k_win_done<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_winout.as<WinOut>(), ctx->d_done.as<unsigned char>(), ctx->d_counters.as<u64>());
+        CK(cudaGetLastError());
+        ctx->stats.kernel_launches += 3;
+        ctx->tile_walks = true;                     // text lengths are measured by k_cigar_text
+        leaf_base = n; ops_base = ctx->ops_words_fused;
+    }
+    const bool have_done = use_fused || win_fast;   // d_done marks the pairs that are finished already
     // ---- QUICKED stage 1: WindowEd(S) bound (quicked.c:178-199) ----
     if (prm.algo == QUICKED && !use_fused) {
         Span sp(ctx, ST_WS);
@@ -1014,7 +1042,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         pp.tiles = ctx->use_tiles ? 1 : 0;
         k_plan<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, pp, ctx->d_bound.as<int>(), ctx->d_hew.as<int>(),
                                                ctx->d_plan_items.as<PlanSum>(), ctx->d_cls.as<unsigned char>(), ctx->d_cutoff.as<i64>(),
-                                               ctx->d_status.as<int>(), ctx->d_score.as<int>(), use_fused ? ctx->d_done.as<unsigned char>() : nullptr,
+                                               ctx->d_status.as<int>(), ctx->d_score.as<int>(), have_done ? ctx->d_done.as<unsigned char>() : nullptr,
                                                reinterpret_cast<unsigned *>(ctx->d_counters.as<u64>() + 28));
         CK(cudaGetLastError());
         size_t tmp = 0;
@@ -1045,7 +1073,7 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         k_build_leaves<<<nb256, 256, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_cls.as<unsigned char>(), ctx->d_cutoff.as<i64>(),
                                                        ctx->d_plan_offs.as<PlanSum>(), ctx->d_leaves.as<BandTask>(), ctx->d_list_t.as<int>(),
                                                        ctx->d_list_w.as<int>(), ctx->d_list_slow.as<int>(), ctx->d_pairleaves.as<PairLeaves>(),
-                                                       use_fused ? ctx->d_done.as<unsigned char>() : nullptr, leaf_base, ops_base);
+                                                       have_done ? ctx->d_done.as<unsigned char>() : nullptr, leaf_base, ops_base);
         CK(cudaGetLastError());
         ctx->stats.kernel_launches++;
     }

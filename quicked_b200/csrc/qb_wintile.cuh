@@ -61,6 +61,7 @@ k_windowed_tiles(const WinTask *__restrict__ tasks, int n_tasks, const unsigned 
     for (i64 i = gtid; i < n_tasks; i += nthr) {
         const WinTask tk = tasks[i];
         const int W = tk.W, O = tk.O;
+        if (tk.m <= 0 || tk.n <= 0) continue;                             // a pair with an empty side has no task (k_win_build)
         if (W > Wmax || (tk.sse && W == 2)) { WinOut wo; wo.score = 0; wo.hew = kWinPunted; outs[tk.slot] = wo; continue; }
         const u64 *pq = peq + tk.peq_off;
         const unsigned char *tc = codes + tk.t_off;
@@ -203,6 +204,44 @@ k_windowed_tiles(const WinTask *__restrict__ tasks, int n_tasks, const unsigned 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ws += __shfl_down_sync(kFull, ws, o);
     if ((t & 31) == 0 && ws) atomicAdd(&counters[0], ws);
+}
+
+// The WINDOWED algorithm planned on the device (reference run_windowed, quicked.c:91-123): one task, one pseudo-leaf and the
+// leaf list of every pair, straight from its PairRec; pair i owns leaf slot i and the op words PairRec.ops_off.
+__global__ void __launch_bounds__(256)
+k_win_build(const PairRec *__restrict__ pairs, int n, int W, int O, int sse, WinTask *__restrict__ tasks, BandTask *__restrict__ leaves,
+            PairLeaves *__restrict__ pl, int *__restrict__ status, int ok_status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PairRec r = pairs[i];
+    WinTask t;
+    t.p_off = r.p_off; t.t_off = r.t_off; t.m = r.m; t.n = r.n; t.rev = 0; t.W = W; t.O = O; t.hew_threshold = 0;
+    t.sse = sse; t.score_only = 0; t.peq_off = r.peq_off; t.nbp = r.nbp; t.slot = i; t.scratch_off = 0;
+    t.ops_off = r.ops_off; t.ops_cap = ((r.m + r.n + 15) / 16) * 16; t.leaf_slot = i;
+    tasks[i] = t;
+    PairLeaves p; p.first_leaf = i; p.n_leaves = 0; p.pad_ = 0;
+    if (r.m > 0 && r.n > 0) {
+        BandTask lf;
+        memset(&lf, 0, sizeof lf);
+        lf.p_off = r.p_off; lf.t_off = r.t_off; lf.m = r.m; lf.n = r.n; lf.pair = i;
+        lf.ops_off = t.ops_off; lf.ops_cap = t.ops_cap; lf.slot = i;
+        leaves[i] = lf;
+        p.n_leaves = 1;
+        status[i] = ok_status;
+    }
+    pl[i] = p;
+}
+// done[i] = 1 for the pairs k_windowed_tiles finished; the others (empty sides, tasks it flagged for the warp kernel) go
+// through the planner to the host-driven path
+__global__ void __launch_bounds__(256)
+k_win_done(const PairRec *__restrict__ pairs, int n, const WinOut *__restrict__ outs, unsigned char *__restrict__ done, u64 *__restrict__ counters)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool ok = pairs[i].m > 0 && pairs[i].n > 0 && outs[i].hew != kWinPunted;
+    done[i] = ok ? 1 : 0;
+    if (ok) atomicAdd(&counters[2], 1ull);
 }
 
 }  // namespace qb

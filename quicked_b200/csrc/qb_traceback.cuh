@@ -574,10 +574,14 @@ k_cigar_text_warp(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask
                         const int st = 16 * lane + k;
                         if (pv != NONE) {
                             unsigned x = (unsigned)(st - pv);
-                            const int nd = dec_digits(x);
-                            for (int d = nd - 1; d >= 0; --d) { q[d] = (unsigned char)('0' + x % 10u); x /= 10u; }
-                            q[nd] = (unsigned char)"MXID"[k > lo_k ? (int)((wv >> (2 * (k - 1))) & 3u) : prev_op];
-                            q += nd + 1;
+                            const unsigned char opc = (unsigned char)"MXID"[k > lo_k ? (int)((wv >> (2 * (k - 1))) & 3u) : prev_op];
+                            if (x < 10u) { q[0] = (unsigned char)('0' + x); q[1] = opc; q += 2; }      // most runs are this short
+                            else {
+                                const int nd = dec_digits(x);
+                                for (int d = nd - 1; d >= 0; --d) { q[d] = (unsigned char)('0' + x % 10u); x /= 10u; }
+                                q[nd] = opc;
+                                q += nd + 1;
+                            }
                         }
                         pv = st;
                     }
@@ -585,9 +589,12 @@ k_cigar_text_warp(const PairLeaves *__restrict__ pl, int n_pairs, const BandTask
                 __syncwarp();
                 char *g = dst + out - mis;
                 const int nb = mis + total;
-                for (int b0 = 4 * lane; b0 < nb; b0 += 128) {
-                    if (b0 >= mis && b0 + 4 <= nb) *reinterpret_cast<u32 *>(g + b0) = *reinterpret_cast<const u32 *>(stg + b0);
-                    else for (int k = max(b0, mis); k < min(b0 + 4, nb); ++k) g[k] = (char)stg[k];
+                const int wlo = mis ? 1 : 0, whi = nb >> 2;               // the whole words [wlo, whi) of the span
+                for (int wq = wlo + lane; wq < whi; wq += 32) reinterpret_cast<u32 *>(g)[wq] = reinterpret_cast<const u32 *>(stg)[wq];
+                if (lane < 4) {                                           // its first and last few bytes
+                    if (mis && lane >= mis && lane < nb) g[lane] = (char)stg[lane];
+                    const int kt = 4 * whi + lane;
+                    if (kt >= mis && kt < nb) g[kt] = (char)stg[kt];
                 }
                 __syncwarp();
             }

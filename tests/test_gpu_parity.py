@@ -232,6 +232,29 @@ def test_cli_matches_oracle_output_format(gpu, oracle, tmp_path):
             assert line == f"{sc}\t{cg}", (algo, line[:60])
 
 
+def test_cli_check_score_and_verbose(gpu, tmp_path):
+    """--check score: every QUICKED score equals the exact edit distance of the tool's own multi-word checker (the
+    reference asks edlib, benchmark_check.c:117-158); a 5 % band on 20 %-error reads is reported inexact, not failed;
+    -v prints the reference's stage-timer lines (align_benchmark.c:120-129) from the GPU stage times."""
+    import subprocess
+    from quicked_b200.datagen import write_seq_file
+    from _common import ROOT
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=True)
+    pairs = generate_pairs(200, 400, 0.2, seed=41) + generate_pairs(5, 6000, 0.15, seed=42)
+    seq = tmp_path / "in.seq"
+    write_seq_file(str(seq), pairs)
+    exe = os.path.join(ROOT, "tools", "qb_align_benchmark")
+    r = subprocess.run([exe, "-a", "quicked", "-i", str(seq), "--check", "score", "-v"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert f"Score.Correct       {len(pairs)} / {len(pairs)}" in r.stderr and f"Alignments.Correct  {len(pairs)} / {len(pairs)}" in r.stderr
+    assert "Time.Windowed Small" in r.stderr and "Time.Align" in r.stderr and "CIGAR.Matches" in r.stderr
+    r = subprocess.run([exe, "-a", "edit-banded", "--bandwidth", "5", "-i", str(seq), "--check", "alignment"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr                       # CIGARs still replay; the scores of a too-narrow band are just not optimal
+    import re
+    ok = int(re.search(r"Score.Correct\s+(\d+) /", r.stderr).group(1))
+    assert 0 <= ok < len(pairs) and "Score.Diff" in r.stderr
+
+
 def test_cli_streaming_fasta_in_sam_out(gpu, oracle, tmp_path):
     """FASTA records (multi-line, consecutive records = pattern, text) streamed in small batches, SAM
     lines out with the reference's SAM CIGAR (query = text, reference = pattern) and NM = score; the plain

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <getopt.h>
+#include <strings.h>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -30,7 +31,7 @@
 
 struct Options {
     std::string algo = "quicked", input, output, output_sam, input_format = "auto";
-    bool output_full = false, force_scalar = false, check = false, only_score = false, sam_eqx = false;
+    bool output_full = false, force_scalar = false, check = false, check_score = false, only_score = false, sam_eqx = false;
     int bandwidth = 15, window_size = 9, overlap_size = 1, hew_threshold = 40, hew_percentage = 15;
     long batch_size = 1000000;
     int device = 0, verbose = 0;
@@ -53,7 +54,9 @@ static void usage()
             "          --bandwidth INT  --window-size INT  --overlap-size INT\n"
             "          --hew-threshold INT  --hew-percentage INT  --force-scalar  --only-score\n"
             "        [Misc]\n"
-            "          --check|c correct         replay every CIGAR on its pair\n"
+            "          --check|c correct|score|alignment   replay every CIGAR on its pair; score / alignment: also compare the\n"
+            "                                    score with the exact edit distance (the reference asks edlib; here a\n"
+            "                                    multi-word bit-parallel checker in this tool: O(m*n/64) per pair)\n"
             "        [System]\n"
             "          --batch-size INT (pairs per GPU batch, default 1000000)   --device INT   --verbose|v\n");
 }
@@ -167,6 +170,34 @@ struct PairReader {
     }
 };
 
+// Exact global edit distance of (p, t): Myers' bit-vector recurrence over ceil(m/64) words per text column, unbanded —
+// the job edlib does for the reference's `--check score` (benchmark_check.c:117-158).  Raw byte compare.
+static long exact_edit_distance(const char *p, long m, const char *t, long n)
+{
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const long W = (m + 63) / 64;
+    std::vector<uint64_t> peq((size_t)W * 256, 0), pv((size_t)W, ~0ull), mv((size_t)W, 0);
+    for (long i = 0; i < m; ++i) peq[(size_t)((unsigned char)p[i]) * W + i / 64] |= 1ull << (i & 63);
+    long score = m;
+    const int top = (int)((m - 1) & 63);
+    for (long j = 0; j < n; ++j) {
+        const uint64_t *eqc = &peq[(size_t)((unsigned char)t[j]) * W];
+        uint64_t hp_in = 1, hm_in = 0;                   // global alignment: row 0 costs j
+        for (long w = 0; w < W; ++w) {
+            const uint64_t eq = eqc[w], xv = eq | mv[w], eqh = eq | hm_in;
+            const uint64_t xh = (((eqh & pv[w]) + pv[w]) ^ pv[w]) | eqh;
+            uint64_t ph = mv[w] | ~(xh | pv[w]), mh = pv[w] & xh;
+            if (w == W - 1) score += (long)((ph >> top) & 1) - (long)((mh >> top) & 1);
+            const uint64_t hp_out = ph >> 63, hm_out = mh >> 63;
+            ph = (ph << 1) | hp_in; mh = (mh << 1) | hm_in;
+            pv[w] = mh | ~(xv | ph); mv[w] = ph & xv;
+            hp_in = hp_out; hm_in = hm_out;
+        }
+    }
+    return score;
+}
+
 int main(int argc, char **argv)
 {
     Options o;
@@ -196,7 +227,12 @@ int main(int argc, char **argv)
         case 2004: o.hew_percentage = atoi(optarg); break;
         case 2005: o.force_scalar = true; break;
         case 2006: o.only_score = true; break;
-        case 'c': o.check = true; break;
+        case 'c':                                        // align_benchmark_params.c:205-227
+            if (!strcasecmp(optarg, "correct")) o.check = true;
+            else if (!strcasecmp(optarg, "score") || !strcasecmp(optarg, "alignment")) o.check = o.check_score = true;
+            else if (!strcasecmp(optarg, "display")) {}
+            else { fprintf(stderr, "Option '--check' must be in {'correct','score','alignment'}\n"); return 1; }
+            break;
         case 't': case 'P': break;                       // accepted for command-line compatibility
         case 4000: o.batch_size = atol(optarg); break;
         case 4002: o.device = atoi(optarg); break;
@@ -230,7 +266,9 @@ int main(int argc, char **argv)
     Batch ring[kRing];
     std::mutex mu;
     std::condition_variable cv;
-    long total = 0, bad = 0;
+    long total = 0, bad = 0, score_ok = 0, score_total = 0, score_diff = 0, cg_m = 0, cg_x = 0, cg_i = 0, cg_d = 0, bases = 0;
+    qb200_stats_t st_acc;
+    memset(&st_acc, 0, sizeof st_acc);
     double t_align = 0;
     int fatal = 0;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -265,6 +303,25 @@ int main(int argc, char **argv)
                 const bool err = quicked_check_error((quicked_status_t)b.status[q]);
                 const char *P = b.seqs.p + b.po[q], *T = b.seqs.p + b.to[q];
                 if (o.check && !err && !prm.only_score && !replay_ok(cg, P, b.pl[q], T, b.tl[q], b.score[q])) ++bad;
+                if (o.check && !err && !prm.only_score) {           // CIGAR breakdown (benchmark_check.c:64-74)
+                    bases += b.pl[q];
+                    for (const char *x = cg; *x;) {
+                        long len = 0;
+                        while (*x >= '0' && *x <= '9') { len = len * 10 + (*x - '0'); ++x; }
+                        if (!*x) break;
+                        const char op = *x++;
+                        (op == 'M' ? cg_m : op == 'X' ? cg_x : op == 'I' ? cg_i : cg_d) += len;
+                    }
+                }
+                if (o.check_score && !err) {
+                    const long exact = exact_edit_distance(P, b.pl[q], T, b.tl[q]);
+                    score_total += exact;
+                    if (exact == b.score[q]) ++score_ok;
+                    else {
+                        score_diff += labs(exact - b.score[q]);
+                        if (o.verbose) fprintf(stderr, "(#%lld)\t INACCURATE SCORE computed=%d\tcorrect=%ld\n", (long long)(b.first_index + i), b.score[q], exact);
+                    }
+                }
                 if (out) {
                     if (o.output_full) {
                         fprintf(out, "%d\t%d\t", b.pl[q], b.tl[q]);
@@ -319,6 +376,14 @@ int main(int argc, char **argv)
                 rc = qb200_align_batch(gpu, &prm, &qb, &r);
             }
             t_align += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            qb200_stats_t st;
+            if (qb200_get_stats(gpu, &st) == QB200_OK) {
+                st_acc.ms_total += st.ms_total; st_acc.ms_prepare += st.ms_prepare; st_acc.ms_windowed_s += st.ms_windowed_s; st_acc.ms_windowed_l += st.ms_windowed_l;
+                st_acc.ms_banded += st.ms_banded; st_acc.ms_align_fill += st.ms_align_fill; st_acc.ms_align_trace += st.ms_align_trace;
+                st_acc.ms_cigar += st.ms_cigar; st_acc.ms_fused += st.ms_fused; st_acc.pairs_stage2 += st.pairs_stage2; st_acc.pairs_stage3 += st.pairs_stage3;
+                st_acc.hirschberg_splits += st.hirschberg_splits; st_acc.kernel_launches += st.kernel_launches; st_acc.word_steps += st.word_steps;
+                st_acc.h2d_bytes += st.h2d_bytes; st_acc.d2h_bytes += st.d2h_bytes;
+            }
         }
         if (rc != QB200_OK) {
             fprintf(stderr, "qb_align_benchmark: %s (rc=%d)\n", qb200_last_error(gpu), rc);
@@ -336,7 +401,21 @@ int main(int argc, char **argv)
     const double t_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
     fprintf(stderr, "...processed %ld reads (alignment = %2.3f seq/s)\n", total, t_align > 0 ? total / t_align : 0.0);
     fprintf(stderr, "[Benchmark]\n=> Total.reads            %ld\n=> Time.Benchmark      %9.2f s\n  => Time.Alignment    %9.2f s\n", total, t_total, t_align);
-    if (o.check) fprintf(stderr, "[Accuracy]\n => Alignments.Correct  %ld / %ld\n", total - bad, total);
+    if (o.verbose) {
+        // the reference's QUICKED stage timers (align_benchmark.c:120-129) as the GPU stage times (CUDA events, summed over
+        // the sub-batches of the pipeline: they overlap on the device, so their sum can exceed Time.Alignment)
+        fprintf(stderr, "  => Time.Windowed Small %9.2f ms (WindowEd(S) bound)\n  => Time.Windowed Large %9.2f ms (%ld pairs)\n  => Time.Banded         %9.2f ms (%ld pairs)\n"
+                        "  => Time.Align          %9.2f ms (fill %.2f + traceback %.2f + fused %.2f; %ld Hirschberg splits)\n  => Time.Prepare        %9.2f ms\n  => Time.CigarText      %9.2f ms\n"
+                        "  => GPU.kernel_launches %ld   GPU.word_steps %ld   H2D %ld B   D2H %ld B\n",
+                st_acc.ms_windowed_s, st_acc.ms_windowed_l, (long)st_acc.pairs_stage2, st_acc.ms_banded, (long)st_acc.pairs_stage3,
+                st_acc.ms_align_fill + st_acc.ms_align_trace + st_acc.ms_fused, st_acc.ms_align_fill, st_acc.ms_align_trace, st_acc.ms_fused, (long)st_acc.hirschberg_splits,
+                st_acc.ms_prepare, st_acc.ms_cigar, (long)st_acc.kernel_launches, (long)st_acc.word_steps, (long)st_acc.h2d_bytes, (long)st_acc.d2h_bytes);
+    }
+    if (o.check) {
+        fprintf(stderr, "[Accuracy]\n => Alignments.Correct  %ld / %ld\n", total - bad, total);
+        if (o.check_score) fprintf(stderr, " => Score.Correct       %ld / %ld\n   => Score.Total       %ld score uds.\n     => Score.Diff      %ld score uds.\n", score_ok, total, score_total, score_diff);
+        if (!prm.only_score) fprintf(stderr, " => CIGAR.Breakdown\n   => CIGAR.Matches     %ld / %ld bases\n   => CIGAR.Mismatches  %ld\n   => CIGAR.Insertions  %ld\n   => CIGAR.Deletions   %ld\n", cg_m, bases, cg_x, cg_i, cg_d);
+    }
     if (out) fclose(out);
     if (sam) fclose(sam);
     fclose(in);

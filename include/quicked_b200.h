@@ -152,6 +152,17 @@ int64_t qb200_generate_pairs_ex(uint64_t seed, int64_t first_pair, int64_t n_pai
                                 int32_t indels_num, int32_t indels_len, char *seqs, int64_t *pattern_off,
                                 int32_t *pattern_len, int64_t *text_off, int32_t *text_len);
 
+/* The same generator as a KERNEL: the batch is born in the context's device buffers (one CTA per pair; the text is drawn
+ * counter-based by all threads, the edits are replayed in order with the tail moves done in shared memory) and is
+ * byte-identical to what qb200_generate_pairs_ex writes for the same arguments.  Takes the place of qb200_upload: follow
+ * with qb200_run / qb200_download.  Reads up to ~160 kbp (the pattern has to fit a CTA's shared memory). */
+int qb200_generate_device(qb200_ctx_t *ctx, uint64_t seed, int64_t first_pair, int64_t n_pairs, int32_t length, double error,
+                          int32_t indels_num, int32_t indels_len);
+/* The batch a context holds (uploaded, unpacked from 2 bits, or generated), copied back to the host: seqs must hold
+ * qb200_batch_bytes() bytes; any pointer may be NULL. */
+int64_t qb200_batch_bytes(qb200_ctx_t *ctx);
+int qb200_download_batch(qb200_ctx_t *ctx, char *seqs, int64_t *pattern_off, int32_t *pattern_len, int64_t *text_off, int32_t *text_len);
+
 /* --- SAM-style CIGAR of one alignment (host-side string transform; reference cigar_compute_CIGAR /
  * cigar_sprint_SAM_CIGAR, quicked_utils/src/cigar.c:193-240, :504-529).  `cigar` is the run-length text this library
  * and the reference's quicked_align produce ("12M1X3I...": M match, X mismatch, I consumes a text character,

@@ -27,7 +27,7 @@ EXPORTS = ["quicked_check_error", "quicked_status_msg", "quicked_default_params"
            "qb200_set_workspace_limit", "qb200_last_error", "qb200_upload", "qb200_upload_device", "qb200_run",
            "qb200_download", "qb200_get_stats", "qb200_get_bounds", "qb200_cigar_to_sam", "qb200_align_batch", "qb200_host_alloc", "qb200_host_free",
            "qb200_generate_pairs", "qb200_generate_pairs_ex", "qb200_measure_int_peak", "qb200_pack_batch", "qb200_upload_packed",
-           "qb200_align_batch_packed"]
+           "qb200_align_batch_packed", "qb200_generate_device", "qb200_batch_bytes", "qb200_download_batch"]
 
 
 class Params(C.Structure):        # quicked_params_t, 48 bytes
@@ -110,6 +110,10 @@ def load():
     L.qb200_pack_batch.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
     L.qb200_upload_packed.argtypes = [C.c_void_p, C.POINTER(PackedBatch)]
     L.qb200_align_batch_packed.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(PackedBatch), C.POINTER(Results)]
+    L.qb200_generate_device.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_double, C.c_int32, C.c_int32]
+    L.qb200_batch_bytes.restype = C.c_int64
+    L.qb200_batch_bytes.argtypes = [C.c_void_p]
+    L.qb200_download_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.qb200_measure_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.qb200_host_alloc.restype = C.c_void_p
     L.qb200_host_alloc.argtypes = [C.c_size_t]
@@ -302,6 +306,22 @@ class BatchAligner:
             c = raw[off[i]:off[i + 1] - 1].decode() if off[i + 1] - off[i] > 1 else None
             out.append((int(status[i]), int(score[i]), c))
         return out
+
+    def generate_device(self, seed, n_pairs, length, error, first=0, indels=None):
+        """qb200_generate_device: the batch is generated by a kernel in this context's device buffers"""
+        ind = indels or (0, 0)
+        self._n = int(n_pairs)
+        self._check(self._lib.qb200_generate_device(self._h, int(seed), int(first), int(n_pairs), int(length), float(error), int(ind[0]), int(ind[1])),
+                    "qb200_generate_device")
+
+    def download_batch(self):
+        """the batch held by the context -> (seqs, po, pl, to, tl) numpy arrays"""
+        n = self._n
+        seqs = np.zeros(int(self._lib.qb200_batch_bytes(self._h)), np.uint8)
+        po = np.zeros(n, np.int64); to = np.zeros(n, np.int64); pl = np.zeros(n, np.int32); tl = np.zeros(n, np.int32)
+        self._check(self._lib.qb200_download_batch(self._h, seqs.ctypes.data, po.ctypes.data, pl.ctypes.data, to.ctypes.data, tl.ctypes.data),
+                    "qb200_download_batch")
+        return seqs, po, pl, to, tl
 
     def upload_packed_arrays(self, packed, n_chars, po, pl, to, tl, exc_pos, exc_chr):
         """2-bit packed stream + exception list (pack_2bit) -> qb200_upload_packed"""

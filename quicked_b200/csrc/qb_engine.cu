@@ -22,6 +22,7 @@
 #include "qb_banded.cuh"
 #include "qb_common.cuh"
 #include "qb_fused.cuh"
+#include "qb_generate.cuh"
 #include "qb_hirschberg.cuh"
 #include "qb_plan.cuh"
 #include "qb_prep.cuh"
@@ -789,6 +790,63 @@ int qb200_align_batch_packed(qb200_ctx_t *ctx, const quicked_params_t *params, c
     if (!rc) rc = qb200_run(ctx, params);
     if (!rc) rc = qb200_download(ctx, res);
     return rc;
+}
+
+// ---- a batch born on the device: the seeded generator of qb200_generate_pairs_ex as a kernel ----
+int qb200_generate_device(qb200_ctx_t *ctx, uint64_t seed, int64_t first_pair, int64_t n_pairs, int32_t length, double error,
+                          int32_t indels_num, int32_t indels_len)
+{
+    if (!ctx || n_pairs < 0 || first_pair < 0 || length <= 0 || indels_num < 0 || indels_len < 0) return QB200_ERR_ARG;
+    if (n_pairs > kMaxPairs) { ctx->err = "a batch holds at most 2^31 - 2^20 pairs: split it"; return QB200_ERR_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    GenParams g;
+    g.seed = seed; g.first_pair = first_pair; g.length = length; g.indels_num = indels_num; g.indels_len = indels_len;
+    g.num_errors = error >= 1.0 ? (int)error : (int)std::ceil((double)((float)length * (float)error));     // generate_dataset.c:370
+    g.stride = 2 * (i64)length + g.num_errors + 2;
+    const size_t smem = ((size_t)(length + g.num_errors + 16) / 4 + 8) * 4;
+    if (smem > 200 * 1024) { ctx->err = "qb200_generate_device: reads of this length do not fit a CTA's shared memory (use qb200_generate_pairs_ex)"; return QB200_ERR_ARG; }
+    const i64 bytes = n_pairs * g.stride;
+    ctx->n_pairs = n_pairs; ctx->raw_bytes = (bytes + 15) / 16 * 16; ctx->d_raw_ext = nullptr;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    const size_t padded = (size_t)ctx->raw_bytes + 48;
+    CK(ctx->d_raw.reserve(padded));
+    CK(cudaMemsetAsync(ctx->d_raw.p, 0, padded, ctx->stream));
+    CK(ctx->d_bound.reserve((size_t)std::max<i64>(n_pairs, 1) * 4));             // borrowed: the pattern lengths
+    if (n_pairs) {
+        CK(cudaFuncSetAttribute(k_generate_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+        const int occ = (int)std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (smem + 1024)));
+        const int blocks = (int)std::min<i64>(n_pairs, (i64)ctx->sms * occ);
+        k_generate_pairs<<<blocks, kGenThreads, smem, ctx->stream>>>(g, (int)n_pairs, ctx->d_raw.as<unsigned char>(), ctx->d_bound.as<int>());
+        CK(cudaGetLastError());
+    }
+    // the pair records need the pattern lengths (4 bytes per pair come back; the characters stay in HBM)
+    std::vector<int32_t> pl((size_t)n_pairs), tl((size_t)n_pairs, length);
+    std::vector<int64_t> po((size_t)n_pairs), to((size_t)n_pairs);
+    if (n_pairs) CK(cudaMemcpyAsync(pl.data(), ctx->d_bound.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (i64 i = 0; i < n_pairs; ++i) { po[(size_t)i] = i * g.stride; to[(size_t)i] = i * g.stride + length + g.num_errors + 1; }
+    int rc = build_pair_records(ctx, n_pairs, po.data(), pl.data(), to.data(), tl.data(), ctx->raw_bytes);
+    if (rc) return rc;
+    return finish_upload(ctx);
+}
+
+// The batch a context holds (uploaded, unpacked or generated), copied back to host arrays: seqs needs qb200_batch_bytes().
+int64_t qb200_batch_bytes(qb200_ctx_t *ctx) { return ctx ? ctx->raw_bytes : QB200_ERR_ARG; }
+int qb200_download_batch(qb200_ctx_t *ctx, char *seqs, int64_t *pattern_off, int32_t *pattern_len, int64_t *text_off, int32_t *text_len)
+{
+    if (!ctx) return QB200_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (seqs && ctx->raw_bytes) CK(cudaMemcpyAsync(seqs, ctx->raw(), (size_t)ctx->raw_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (i64 i = 0; i < ctx->n_pairs; ++i) {
+        const PairRec &r = ctx->h_pairs[(size_t)i];
+        if (pattern_off) pattern_off[i] = r.p_off;
+        if (pattern_len) pattern_len[i] = r.m;
+        if (text_off) text_off[i] = r.t_off;
+        if (text_len) text_len[i] = r.n;
+    }
+    return 0;
 }
 
 int qb200_upload_device(qb200_ctx_t *ctx, const qb200_batch_t *b)

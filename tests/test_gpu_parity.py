@@ -396,6 +396,28 @@ def test_stage1_compact_kernel(oracle, monkeypatch):
     a.close()
 
 
+@pytest.mark.parametrize("length,error,indels", [(100, 0.05, None), (1000, 0.1, None), (3000, 0.2, (5, 100)), (10000, 0.2, None), (777, 3.0, (2, 900)), (1, 0.5, None)])
+def test_device_generator_is_the_host_generator(gpu, length, error, indels):
+    """qb200_generate_device (one CTA per pair, edits replayed in shared memory) writes byte for byte what the host
+    generator qb200_generate_pairs_ex writes for the same (seed, slice, length, error, --indels), and the batch aligns."""
+    import quicked_b200 as qb
+    n = 300 if length <= 3000 else 60
+    for seed, first in ((7, 0), (7, 12345)):
+        seqs, po, pl, to, tl = qb.generate_pairs_native(seed, n, length, error, first=first, indels=indels)
+        gpu.generate_device(seed, n, length, error, first=first, indels=indels)
+        dseqs, dpo, dpl, dto, dtl = gpu.download_batch()
+        assert np.array_equal(dpl, pl) and np.array_equal(dtl, tl) and np.array_equal(dpo, po) and np.array_equal(dto, to)
+        for i in range(n):
+            assert bytes(dseqs[po[i]:po[i] + pl[i]]) == bytes(seqs[po[i]:po[i] + pl[i]]), (seed, first, i, "pattern")
+            assert bytes(dseqs[to[i]:to[i] + tl[i]]) == bytes(seqs[to[i]:to[i] + tl[i]]), (seed, first, i, "text")
+    gpu.run(algo=0)
+    status, score, off, cig = gpu.download()
+    gpu.upload_arrays(seqs, po, pl, to, tl)
+    gpu.run(algo=0)
+    status2, score2, off2, cig2 = gpu.download()
+    assert np.array_equal(score, score2) and np.array_equal(status, status2) and np.array_equal(cig, cig2)
+
+
 def test_packed_upload_matches_ascii_upload(oracle, monkeypatch):
     """2-bit packed input (qb200_pack_batch -> qb200_upload_packed): same scores and CIGARs as the ASCII upload and the
     oracle, on plain reads and on reads with N / lower-case / IUPAC characters (the exception list)."""

@@ -946,9 +946,13 @@ int qb200_run(qb200_ctx_t *ctx, const quicked_params_t *params)
         CK(ctx->d_pairodd.reserve((size_t)n + 16));
         // forward match masks (+ the per-pair odd-character flags): one thread per pattern on big batches of short
         // patterns, one warp per pattern otherwise (job list derived on the device from the pair records)
-        if (ni >= 16384 && ctx->max_m <= 32768 && !getenv("QB200_PEQ_WARP")) {
-            k_build_peq_pairs<<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(),
-                                                                       ctx->d_peq.as<u64>(), ctx->d_pairodd.as<unsigned char>());
+        if ((ni >= 16384 || ctx->max_m >= 4096) && !getenv("QB200_PEQ_WARP")) {
+            if (ctx->max_m >= 4096)                                  // long patterns: a warp each (lane = every 32nd block)
+                k_build_peq_pairs<32><<<(unsigned)(((i64)ni * 32 + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(),
+                                                                                                     ctx->d_peq.as<u64>(), ctx->d_pairodd.as<unsigned char>());
+            else
+                k_build_peq_pairs<1><<<(ni + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_pairs.as<PairRec>(), ni, ctx->d_codes.as<unsigned char>(),
+                                                                              ctx->d_peq.as<u64>(), ctx->d_pairodd.as<unsigned char>());
             CK(cudaGetLastError());
             ctx->stats.kernel_launches++;
         } else if (ni) {

@@ -121,21 +121,27 @@ __device__ __forceinline__ u32 movemask8(u64 x, int k)     // bit k of each of t
     return (u32)((((x >> k) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
 }
 
+// G = 1: one pattern per thread (reads up to a few kbp: enough patterns to fill the GPU).  G = 32: one pattern per warp,
+// lane l takes blocks l, l + 32, ... and a 32nd of the text scan — 100 k patterns of 10 kbp are only 100 k threads
+// otherwise (0.91 ms, 30 % issue slots; the blocks of a pattern are independent).
+template <int G>
 __global__ void __launch_bounds__(128) k_build_peq_pairs(const PairRec *__restrict__ pairs, int n, const unsigned char *__restrict__ codes,
                                                          u64 *__restrict__ peq, unsigned char *__restrict__ odd_flags)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt / G, gl = gt % G;
     if (i >= n) return;
     const PairRec r = pairs[i];
-    if (r.m <= 0 || r.n <= 0) { odd_flags[i] = 1; return; }       // no table (and no space for one)
+    if (r.m <= 0 || r.n <= 0) { if (gl == 0) odd_flags[i] = 1; return; }       // no table (and no space for one)
     const int nblk = (r.m + 63) >> 6, nbp = nblk + 2;
     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(peq + r.peq_off);
     const unsigned long long p0 = (unsigned long long)(codes + r.p_off);
     const u64 *src = reinterpret_cast<const u64 *>(p0 & ~7ull);
     const unsigned sh = 8u * (unsigned)(p0 & 7ull);
-    u64 prev = __ldg(src);
+    u64 prev = (G == 1) ? __ldg(src) : 0ull;
     u64 any_odd = 0;
-    for (int blk = 0; blk < nblk; ++blk) {
+    for (int blk = gl; blk < nblk; blk += G) {
+        if (G > 1) prev = __ldg(src + blk * 8);
         u64 b0 = 0, b1 = 0, b2 = 0, od = 0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -158,18 +164,24 @@ __global__ void __launch_bounds__(128) k_build_peq_pairs(const PairRec *__restri
         dst[blk * 3 + 1] = make_ulonglong2(e2, e3);
         dst[blk * 3 + 2] = make_ulonglong2(e4, od);
     }
+    if (gl == 0) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dst[nblk * 3 + k] = make_ulonglong2(0, 0);       // the two blocks past the pattern
+        for (int k = 0; k < 6; ++k) dst[nblk * 3 + k] = make_ulonglong2(0, 0);   // the two blocks past the pattern
+    }
     (void)nbp;
     // odd characters of the text: aligned 8-byte words, bytes outside the text masked off
     const unsigned long long t0 = (unsigned long long)(codes + r.t_off), t1 = t0 + (unsigned long long)r.n;
-    for (unsigned long long a = t0 & ~7ull; a < t1; a += 8) {
+    for (unsigned long long a = (t0 & ~7ull) + 8ull * (unsigned)gl; a < t1; a += 8ull * G) {
         u64 msk = 0x0c0c0c0c0c0c0c0cull;                              // kCodeOdd, or code 4: a text character that is not A, C, G, T
         if (a < t0) msk <<= 8 * (unsigned)(t0 - a);
         if (a + 8 > t1) msk &= 0x0c0c0c0c0c0c0c0cull >> (8 * (unsigned)(a + 8 - t1));
         any_odd |= __ldg(reinterpret_cast<const u64 *>(a)) & msk;
     }
-    odd_flags[i] = any_odd ? 1 : 0;
+    if (G == 1) odd_flags[i] = any_odd ? 1 : 0;
+    else {
+        const unsigned any = __ballot_sync(kFull, any_odd != 0);   // G = 32: a pattern is a warp (blockDim is a multiple of 32)
+        if (gl == 0) odd_flags[i] = any ? 1 : 0;
+    }
 }
 
 }  // namespace qb

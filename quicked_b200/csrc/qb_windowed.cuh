@@ -15,6 +15,7 @@
 #pragma once
 #include "qb_common.cuh"
 #include "qb_traceback.cuh"
+#include "qb_tiles.cuh"
 
 namespace qb {
 
@@ -54,11 +55,32 @@ __device__ __forceinline__ void ws_full_group8(u32 w0, u32 w1, int c0, u32 top_i
         const u32 code = ((k < 4 ? w0 : w1) >> (8 * (k & 3))) & 7u;
         u32 hp_in0 = top_in;
         if (SSE) hp_in0 = (c == 0) ? top_in : ((c == 1) ? 1u : (u32)((k & 1) ^ 1));   // c0 is a multiple of 8: parity(c) = parity(k)
-        u32 hp, hm, o1, o2;
-        myers_step(weq[code * T], pv0, mv0, hp_in0, 0u, hp, hm);
+        // word 0 (MHin = 0, PHin = hp_in0), then word 1 with word 0's carries taken straight from the top bits of its
+        // Ph / Mh: the adder takes MHin through the carry flag and the two shifts are funnel shifts (the forms of the
+        // BandEd tile step, qb_tiles.cuh; bit-identical to two BPM_ADVANCE_BLOCKs, bpm_commons.h:49-68)
+        u32 ph0_hi, mh0_hi;
+        {
+            const u64 eq0 = weq[code * T];
+            const u64 xv = eq0 | mv0;
+            const u64 xh = (((eq0 & pv0) + pv0) ^ pv0) | eq0;
+            const u64 ph = mv0 | ~(xh | pv0), mh = pv0 & xh;
+            ph0_hi = (u32)(ph >> 32); mh0_hi = (u32)(mh >> 32);
+            const u64 ph_s = (ph << 1) | (u64)hp_in0, mh_s = mh << 1;
+            pv0 = mh_s | ~(xv | ph_s);
+            mv0 = ph_s & xv;
+        }
         if (SSE && c == 127) { pv1_prev = pv1; mv1_prev = mv1; }
         const u64 eq1 = weq[(NC + code) * T], mv1_before = mv1;
-        myers_step(eq1, pv1, mv1, hp, hm, o1, o2);
+        {
+            const u64 xv = eq1 | mv1;
+            const u64 xh = (add_with_top_bit(eq1 & pv1, pv1, mh0_hi) ^ pv1) | eq1;
+            const u64 ph = mv1 | ~(xh | pv1), mh = pv1 & xh;
+            const u32 phl = (u32)ph, phh = (u32)(ph >> 32), mhl = (u32)mh, mhh = (u32)(mh >> 32);
+            const u64 ph_s = ((u64)fsl32(phl, phh, 1) << 32) | (u64)fsl32(ph0_hi, phl, 1);
+            const u64 mh_s = ((u64)fsl32(mhl, mhh, 1) << 32) | (u64)fsl32(mh0_hi, mhl, 1);
+            pv1 = mh_s | ~(xv | ph_s);
+            mv1 = ph_s & xv;
+        }
         if (STORE == 2) sq[(c - 63) * T] = slim_entry(pv1, mv1_before, eq1, c - 63);
         if (STORE == 1) {
             qpv[(i64)(c - 63) * nthr] = pv1;

@@ -234,7 +234,7 @@ def test_cli_matches_oracle_output_format(gpu, oracle, tmp_path):
 
 def test_cli_check_score_and_verbose(gpu, tmp_path):
     """--check score: every QUICKED score equals the exact edit distance of the tool's own multi-word checker (the
-    reference asks edlib, benchmark_check.c:117-158); a 5 % band on 20 %-error reads is reported inexact, not failed;
+    reference asks edlib, benchmark_check.c:117-158); a 1 % band on reads with 200-long deletions is reported inexact, not failed;
     -v prints the reference's stage-timer lines (align_benchmark.c:120-129) from the GPU stage times."""
     import subprocess
     from quicked_b200.datagen import write_seq_file
@@ -248,11 +248,12 @@ def test_cli_check_score_and_verbose(gpu, tmp_path):
     assert r.returncode == 0, r.stderr
     assert f"Score.Correct       {len(pairs)} / {len(pairs)}" in r.stderr and f"Alignments.Correct  {len(pairs)} / {len(pairs)}" in r.stderr
     assert "Time.Windowed Small" in r.stderr and "Time.Align" in r.stderr and "CIGAR.Matches" in r.stderr
-    r = subprocess.run([exe, "-a", "edit-banded", "--bandwidth", "5", "-i", str(seq), "--check", "alignment"], capture_output=True, text=True)
+    write_seq_file(str(seq), pairs + generate_pairs(30, 3000, 0.05, seed=43, indels=(4, 200)))       # 200-long deletions against a 1 % band
+    r = subprocess.run([exe, "-a", "edit-banded", "--bandwidth", "1", "-i", str(seq), "--check", "alignment"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr                       # CIGARs still replay; the scores of a too-narrow band are just not optimal
     import re
     ok = int(re.search(r"Score.Correct\s+(\d+) /", r.stderr).group(1))
-    assert 0 <= ok < len(pairs) and "Score.Diff" in r.stderr
+    assert ok <= len(pairs) + 10 and "Score.Diff" in r.stderr          # at least 20 of the 30 indel pairs are inexact
 
 
 def test_cli_streaming_fasta_in_sam_out(gpu, oracle, tmp_path):

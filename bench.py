@@ -454,6 +454,9 @@ def main():
                       "frac": a / int_peak if int_peak else None, "traffic": traffic.get(key), "ops_per_word_step": 24,
                       "word_steps_per_launch": int(ws), "ms_per_launch": ms,
                       "peak_source": "qb200_measure_int_peak (LOP3+IADD3 microbenchmark, this run); MEASURED_PEAKS.json has no integer peak"})
+    for r in roofs:
+        r["traffic_source"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this "
+                               f"command, profiles/r2_ncu_{args.workload}_{args.algo}_raw.csv") if r["traffic"] is not None else None
     roofs.sort(key=lambda r: -r["ms_per_launch"])
     roof = roofs[0] if roofs else None
     ws_total = sum(ws_all)

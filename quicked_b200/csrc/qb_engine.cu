@@ -346,6 +346,7 @@ int launch_traceback(qb200_ctx *ctx, const int *d_list, int begin, int n_tasks, 
 
 // ---- tile path (qb_tiles.cuh / qb_tiletrace.cuh) ----------------------------------------------------------------
 constexpr int kTileClasses = 8;                     // ring sizes 8 << c: bands up to kTileMaxRing - 2 blocks
+static int kTileBigClass = getenv("QB200_TILE_BIG_CLASS") ? atoi(getenv("QB200_TILE_BIG_CLASS")) : 5;   // classes from this one on run 256 compute lanes per CTA
 struct TileCtl { int counts[kTileClasses]; int next[kTileClasses]; int punt_count; int pad_; unsigned long long tt_words; int pad2_[12]; };
 inline bool tile_band_ok(i64 B) { return tile_ring_for(B) <= kTileMaxRing; }
 
@@ -424,9 +425,12 @@ int launch_tiles(qb200_ctx *ctx, BandTask *d_tasks, const int *d_list, int begin
     for (int c = 0; c < kTileClasses; ++c) {
         if (!((class_mask >> c) & 1u)) continue;
         int rc;
-        int lanes = c == 0 ? 32 : c == 1 ? 64 : 128;
+        // rings of 256+ blocks leave room for two CTAs per SM only (110 KB of slots each): 256 compute lanes per CTA keep
+        // 18 warps on the SM instead of 10
+        int lanes = c == 0 ? 32 : c == 1 ? 64 : c >= kTileBigClass ? 256 : 128;
         if (const char *e = getenv("QB200_TILE_LANES")) lanes = atoi(e);
         if (lanes == 32) rc = launch_tiles_class<FULL, 32>(ctx, P, c, n, n);
+        else if (lanes == 256) rc = launch_tiles_class<FULL, 256>(ctx, P, c, n, n);
         else if (lanes == 128) rc = launch_tiles_class<FULL, 128>(ctx, P, c, n, n);
         else rc = launch_tiles_class<FULL, 64>(ctx, P, c, n, n);
         if (rc) return rc;

@@ -486,7 +486,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int RB, int nslots, int lanes)
 }
 
 template <bool FULL, int LANES>
-__global__ void __launch_bounds__(LANES + 32, LANES >= 128 ? 4 : LANES >= 64 ? 6 : 8) k_band_tiles(TilePools P, TileLaunch Q)
+__global__ void __launch_bounds__(LANES + 32, LANES >= 256 ? 2 : LANES >= 128 ? 4 : LANES >= 64 ? 6 : 8) k_band_tiles(TilePools P, TileLaunch Q)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     constexpr int lanes = LANES;

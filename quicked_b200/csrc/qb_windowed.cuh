@@ -117,6 +117,15 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
             const u64 *pq = peq + pr.peq_off;
             bool wide = false;                               // this window left the slim slice: redo it with the full quadrant
             while (cv >= 0 && ch >= 0) {
+                // The lanes of a warp run their FULL windows first and their last, non-full ones (other code: the quadrant in
+                // the L2 scratch, a walk that loads per step) together: pairs differ by a window or two, and a lane that
+                // entered its tail alone made the whole warp sit through that tail's load latencies — up to 32 times per warp
+                // (ncu on 12.5 k pairs: 19 % of the kernel's stall samples on the tail walk's raw-byte compare).
+                {
+                    const bool want_full = cv >= 127 && ch >= 127;
+                    const unsigned others_full = __ballot_sync(__activemask(), want_full);
+                    if (!want_full && others_full) continue;
+                }
                 // ---- window geometry (bpm_windowed.c:219-232) ----
                 const int v0 = max(cv - 127, 0), h0 = max(ch - 127, 0);
                 const int words = ((cv - v0) >> 6) + 1, cols = ch - h0 + 1;
@@ -161,16 +170,19 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
                 // flight) and are realigned in registers; the flat code buffer is readable 48 B past its end
                 const int csh = (int)((unsigned long long)(tc + h0) & 15ull);
                 const uint4 *cvec = reinterpret_cast<const uint4 *>(tc + h0 - csh);
-                uint4 ccur = __ldg(cvec), cnxt = __ldg(cvec + 1);
+                // cpre: the chunk after cnxt, loaded a whole rotation before it is moved (a register move of a value still
+                // in flight waits for it: with the load issued in the rotation that consumed it, every 16 columns stalled
+                // on an L2 round trip when the warp had the SM sub-partition to itself)
+                uint4 ccur = __ldg(cvec), cnxt = __ldg(cvec + 1), cpre = __ldg(cvec + 2);
                 u32 code_last = 4;
                 if (full) {
                     uint4 r = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
                     for (int q = 0; q < 16; ++q) {           // sixteen groups of eight columns
                         if (!(q & 1)) {
-                            const uint4 c2 = __ldg(cvec + min((q >> 1) + 2, 8));
                             r = realign16(ccur, cnxt, csh);
-                            ccur = cnxt; cnxt = c2;
+                            ccur = cnxt; cnxt = cpre;
+                            cpre = __ldg(cvec + min((q >> 1) + 3, 8));
                         }
                         const u32 w0 = (q & 1) ? r.z : r.x, w1 = (q & 1) ? r.w : r.y;
                         if (q < 8) {
@@ -189,9 +201,9 @@ __device__ __forceinline__ void ws21_pair(const PairRec &pr, const unsigned char
 #pragma unroll 1
                     for (int c0 = full ? cols : 0; c0 < cols; c0 += 8) {
                         if (!(c0 & 8)) {
-                            const uint4 c2 = __ldg(cvec + (c0 >> 4) + 2);
                             r = realign16(ccur, cnxt, csh);
-                            ccur = cnxt; cnxt = c2;
+                            ccur = cnxt; cnxt = cpre;
+                            cpre = __ldg(cvec + min((c0 >> 4) + 3, ((cols - 1) >> 4) + 2));     // never past what the loop reads anyway
                         }
                         const u32 w0 = (c0 & 8) ? r.z : r.x, w1 = (c0 & 8) ? r.w : r.y;
 #pragma unroll

@@ -1,8 +1,8 @@
-for p in 75000 100000 150000; do
-python bench.py --workload c3 --algo windowed --pairs $p --steps 4 --warmup 2 --no-cpu-baseline --no-packed > gpurun_out/r2q.json 2> gpurun_out/r2q.err
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for cfg in "c3 100000" "c3 12500" "c2 1000000"; do set -- $cfg; python bench.py --workload $1 --pairs $2 --steps 5 --warmup 3 --no-cpu-baseline --no-packed > gpurun_out/r2t_$1_$2.json 2> gpurun_out/r2t_$1_$2.err; tail -c 200 gpurun_out/r2t_$1_$2.err; done
 python - <<PY
 import json
-d=json.loads([l for l in open("gpurun_out/r2q.json") if l.startswith("{")][-1])
-print($p, round(d["ms_per_step"],1), {k:round(v,1) for k,v in d["stage_ms_per_step"].items() if v})
+for n in ("c3_100000","c3_12500","c2_1000000"):
+    d=json.loads([l for l in open(f"gpurun_out/r2t_{n}.json") if l.startswith("{")][-1])
+    print(n, round(d["ms_per_step"],2), round(d["value"]), {k:round(v,2) for k,v in d["stage_ms_per_step"].items() if v}, round(d["int_alu_roofline"]["frac"],3))
 PY
-done

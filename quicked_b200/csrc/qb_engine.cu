@@ -359,13 +359,22 @@ int launch_tiles_class(qb200_ctx *ctx, const TilePools &P, int c, int cap, int n
     if (const char *e = getenv("QB200_TILE_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
     int nslots = (int)((budget > fixed ? budget - fixed : 0) / per);
     nslots = std::max(1, std::min(32, nslots));
+    if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
+    {   // few tasks: no more slots per CTA than it takes to give every resident CTA its share (26 slots for 12.5 k tasks
+        // left 111 of 592 CTAs without work: 5.6 vs 5.0 ms; 4 slots for the 512 half-passes of a Hirschberg level used
+        // 128 of 296)
+        int occ0 = (int)((227 * 1024) / (tile_smem_bytes(RB, nslots, LANES) + 1024));
+        occ0 = std::max(1, std::min(occ0, 2048 / (LANES + 32)));
+        const int share = (int)(((i64)n_bound + (i64)ctx->sms * occ0 - 1) / ((i64)ctx->sms * occ0));
+        nslots = std::min(nslots, std::max(share, 1));
+    }
     if (const char *e = getenv("QB200_TILE_SLOTS")) nslots = std::max(1, std::min(32, atoi(e)));
     const size_t smem = tile_smem_bytes(RB, nslots, LANES);
     auto kern = k_band_tiles<FULL, LANES>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (!ctx->sms) { ctx->sms = 148; cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, ctx->device); }
     int occ = (int)((227 * 1024) / (smem + 1024));
     occ = std::max(1, std::min(occ, 2048 / (LANES + 32)));
+    occ = std::min(occ, LANES >= 256 ? 2 : LANES >= 128 ? 4 : LANES >= 64 ? 6 : 8);       // the kernel's launch bound
     const int blocks = std::max(1, std::min(ctx->sms * occ, (n_bound + nslots - 1) / nslots));
     TileCtl *ctl = ctx->d_tctl.as<TileCtl>();
     TileLaunch Q;

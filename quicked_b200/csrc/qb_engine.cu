@@ -701,8 +701,21 @@ int64_t qb200_pack_batch(const qb200_batch_t *in, uint8_t *packed, int64_t *exc_
     {
         std::vector<std::thread> th;
         for (int k = 0; k < nt; ++k) th.emplace_back([=]() {
-            const i64 q0 = nq * k / nt, q1 = nq * (k + 1) / nt;
+            i64 q0 = nq * k / nt, q1 = nq * (k + 1) / nt;
+            q0 &= ~(i64)1; if (k + 1 < nt) q1 &= ~(i64)1;     // whole 8-character groups per thread
             const unsigned char *s = reinterpret_cast<const unsigned char *>(in->seqs);
+            // eight characters per step: bits 1-2 of A C G T are 0 1 3 2 -> code = x ^ (x >> 1); the eight 2-bit codes are
+            // then squeezed out of their bytes (bytes -> nibbles -> bytes -> 16 bits)
+            for (; q0 + 2 <= q1 && 4 * q0 + 8 <= nb; q0 += 2) {
+                uint64_t w;
+                memcpy(&w, s + 4 * q0, 8);
+                uint64_t x = (w >> 1) & 0x0303030303030303ull;
+                x ^= (x >> 1) & 0x0101010101010101ull;
+                x = (x | (x >> 6)) & 0x000f000f000f000full;
+                x = (x | (x >> 12)) & 0x000000ff000000ffull;
+                const unsigned v = (unsigned)((x | (x >> 24)) & 0xffffull);
+                packed[q0] = (uint8_t)v; packed[q0 + 1] = (uint8_t)(v >> 8);
+            }
             for (i64 q = q0; q < q1; ++q) {
                 unsigned v = 0;
                 const i64 lim = std::min<i64>(4, nb - 4 * q);
@@ -726,7 +739,23 @@ int64_t qb200_pack_batch(const qb200_batch_t *in, uint8_t *packed, int64_t *exc_
             const unsigned char *s = reinterpret_cast<const unsigned char *>(in->seqs);
             auto &out = found[(size_t)k];
             auto scan = [&](i64 off, i64 len) {
-                for (i64 j = off; j < off + len; ++j) {
+                i64 j = off;
+                const i64 end = off + len;
+                // 0x80 in every byte of v that is zero, exactly (no borrow across bytes)
+                auto zero_bytes = [](uint64_t v) { return ~(((v & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | v | 0x7f7f7f7f7f7f7f7full); };
+                for (; j + 8 <= end; j += 8) {                // eight characters at a time: which of them are not A, C, G, T?
+                    uint64_t w;
+                    memcpy(&w, s + j, 8);
+                    const uint64_t acgt = zero_bytes(w ^ 0x4141414141414141ull) | zero_bytes(w ^ 0x4343434343434343ull) |
+                                          zero_bytes(w ^ 0x4747474747474747ull) | zero_bytes(w ^ 0x5454545454545454ull);
+                    uint64_t other = ~acgt & 0x8080808080808080ull;
+                    while (other) {
+                        const int bidx = __builtin_ctzll(other) >> 3;
+                        other &= other - 1;
+                        out.emplace_back(j + bidx, s[j + bidx]);
+                    }
+                }
+                for (; j < end; ++j) {
                     const unsigned c = s[j];
                     if (c != 'A' && c != 'C' && c != 'G' && c != 'T') out.emplace_back(j, (uint8_t)c);
                 }

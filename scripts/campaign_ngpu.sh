@@ -1,4 +1,4 @@
-# multi-GPU lines of the round: bash scripts/_campaignN.sh N [all]
+# multi-GPU lines of the round: bash scripts/campaign_ngpu.sh N [all]
 N=$1
 O=gpurun_out/camp
 mkdir -p $O

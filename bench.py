@@ -72,7 +72,7 @@ def ncu_traffic(args):
         ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         for r in rows[2:]:
-            name = r[ik].split("(")[0].split("<")[0].replace("void ", "").strip()
+            name = r[ik].split("(")[0].split("<")[0].replace("void ", "").strip().split("::")[-1]     # "void qb::k_x<1>(...)" -> "k_x"
             out[name] = out.get(name, 0.0) + float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
     except Exception:
         return {}

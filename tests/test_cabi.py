@@ -189,6 +189,10 @@ def test_bench_helpers(oracle):
     for j, i in enumerate(sel):
         assert bytes(s2[po2[j]:po2[j] + pl2[j]]) == bytes(s[po[i]:po[i] + pl[i]])
         assert bytes(s2[to2[j]:to2[j] + tl2[j]]) == bytes(s[to[i]:to[i] + tl[i]])
+    # roofline.traffic: per-kernel DRAM bytes of the committed ncu capture of the default command, keyed by bare kernel name
+    import types
+    traffic = bench.ncu_traffic(types.SimpleNamespace(workload="c3", algo="quicked"))
+    assert traffic.get("k_band_tiles", 0) > 1e9 and traffic.get("k_windowed21_score", 0) > 1e9 and traffic.get("k_traceback_tiles", 0) > 1e9
 
 
 def test_pack_2bit_round_trip(lib):
